@@ -1,0 +1,209 @@
+/*
+ * chemeleon_b200.h -- C-ABI of libchemeleon_b200.so
+ *
+ * B200 (sm_100a) kernels for the reverse-diffusion sampling path of
+ * ryannduma/chemeleon.  The reference is pure Python/PyTorch and has no FFI or
+ * plugin layer of its own, so each entry point below cites the
+ * reference *function* it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C: POD structs of raw pointers + sizes, no torch / C++ types;
+ *  - every buffer (weights, state, outputs, workspace) is CALLER-OWNED; the
+ *    library never allocates or frees device memory;
+ *  - pointers are DEVICE pointers unless the field name starts with `host_`;
+ *  - kernels are enqueued on the given stream (a cudaStream_t passed as void*)
+ *    and never synchronise, so every call is CUDA-graph capturable;
+ *  - return 0 on success, a negative cb2_status otherwise; cb2_last_error()
+ *    returns a thread-local description.  Unsupported shapes / a non-sm_100
+ *    device are hard errors: there is no fallback path of any kind.
+ */
+#ifndef CHEMELEON_B200_H
+#define CHEMELEON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB2_ABI_VERSION 1
+#define CB2_HIDDEN 512
+#define CB2_MAX_LAYERS 16
+#define CB2_MAX_ATOM_TYPES 104
+#define CB2_NUM_FREQS 128
+#define CB2_HEAD_COLS 128       /* type logits 0..103, coord 104..106, zero pad */
+#define CB2_COEF_COLS 16        /* columns of the per-timestep coefficient table */
+#define CB2_TILE_ROWS 128       /* edge rows per tensor-core tile */
+
+typedef enum {
+  CB2_OK = 0,
+  CB2_ERR_BAD_ARG = -1,
+  CB2_ERR_UNSUPPORTED = -2,     /* shape / mode the kernels are not built for */
+  CB2_ERR_CUDA = -3,
+  CB2_ERR_DEVICE = -4,          /* not an sm_100 device */
+  CB2_ERR_WORKSPACE = -5
+} cb2_status;
+
+typedef enum {
+  CB2_PRECISION_FP32 = 0,       /* exact mode: CUDA-core fp32 kernels */
+  CB2_PRECISION_TC_F16 = 1      /* tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate) */
+} cb2_precision;
+
+/* ---- weights of one CSPLayer (cspnet.py:100-181), W1 split by input block ---- */
+typedef struct {
+  const float *w_hij;   /* [1024,512] rows 0:512 = W1[:,0:512] (h_i), 512:1024 = W1[:,512:1024] (h_j) */
+  const float *w_ip;    /* [512,9]    W1[:,1024:1033]  (lattice inner products, row-major 3x3) */
+  const float *b1;      /* [512] */
+  const float *w_fd;    /* [512,768]  W1[:,1033:1801]  (sinusoid embedding, reference column order) */
+  const float *w2;      /* [512,512]  edge_mlp.2 */
+  const float *b2;
+  const float *wn1;     /* [512,1024] node_mlp.0 */
+  const float *bn1;
+  const float *wn2;     /* [512,512]  node_mlp.2 */
+  const float *bn2;
+  const float *ln_g;    /* CSPLayer.layer_norm */
+  const float *ln_b;
+  /* fp16 tcgen05 operand images [K/8][rows][8]; NULL when only exact mode is used */
+  const void *w_hij_t, *w_fd_t, *w2_t, *wn1_t, *wn2_t;
+} cb2_layer_weights;
+
+/* ---- the CSPNet decoder (cspnet.py:184-405) ---- */
+typedef struct {
+  int32_t abi_version;  /* CB2_ABI_VERSION */
+  int32_t hidden;       /* must be 512 */
+  int32_t n_layers;
+  int32_t n_atom_types; /* must be 104 */
+  int32_t n_freqs;      /* must be 128 */
+  int32_t timesteps;    /* T */
+  const float *emb;             /* [104,512] node_embedding (smooth=False) */
+  const float *film_wp;         /* [512,512] FilmLayer.proj */
+  const float *film_bp;
+  const float *film_g;          /* FilmLayer.norm */
+  const float *film_b;
+  const void *film_wp_t;
+  const float *film_time_table; /* [T+1,1024] W_cond[:, :128] @ time_emb(t)  (may be NULL for forward-only use) */
+  cb2_layer_weights layers[CB2_MAX_LAYERS];
+  const float *final_g;         /* final_layer_norm */
+  const float *final_b;
+  const float *w_head;          /* [128,512] rows 0:104 type_out.weight, 104:107 coord_out.weight */
+  const float *b_head;          /* [128] */
+  const void *w_head_t;
+  const float *w_lat;           /* [9,512] lattice_out.weight */
+} cb2_model;
+
+/* ---- topology of one ragged batch; fixed for a whole sampling run ----
+ * Replaces CSPNet.gen_edges (cspnet.py:319-324): edges are implied by the
+ * per-crystal node ranges, no dense adjacency is ever built. */
+typedef struct {
+  int32_t n_nodes;      /* N  = sum of atoms, ONE variant */
+  int32_t n_graphs;     /* B */
+  int32_t n_variants;   /* V: 1, or 2 = [conditional | unconditional] sharing the same state */
+  int32_t max_n;        /* largest crystal */
+  int64_t n_edges;      /* E = sum n^2, ONE variant */
+  const int32_t *node2graph;   /* [N] */
+  const int32_t *node_base;    /* [N] first node of the node's crystal */
+  const int32_t *node_n;       /* [N] atoms in the node's crystal */
+  const int32_t *graph_off;    /* [B+1] node offsets */
+  /* exact path: materialised edge rows in the reference's order (i outer, j inner) */
+  const int32_t *edge_i;       /* [E] */
+  const int32_t *edge_j;       /* [E] */
+  const int64_t *node_eoff;    /* [N+1] edge-row offset of node i's segment */
+  int32_t n_chunks;            /* exact path processes edges in chunks of whole segments */
+  const int32_t *host_chunk_node_lo; /* HOST [n_chunks+1] node boundaries of the chunks */
+  int64_t chunk_max_edges;     /* largest chunk, in edge rows */
+  /* tensor-core path: tiles of 128 edge rows = whole segments of equal length */
+  int32_t n_tiles;
+  const int32_t *tile_row_i;   /* [n_tiles*128] node i of the row, -1 = padding */
+  const int32_t *tile_row_j;   /* [n_tiles*128] node j of the row */
+  const int32_t *tile_seg_n;   /* [n_tiles] segment length (atoms per crystal) of the tile */
+} cb2_batch;
+
+/* ---- one decoder forward: CSPNet.forward (cspnet.py:345-405) ---- */
+typedef struct {
+  const int64_t *atom_types;   /* [N] */
+  const float *frac_coords;    /* [N,3] */
+  const float *lattices;       /* [B,9] row-major 3x3 */
+  const float *film_cond;      /* [V*B,1024] SiLU(mlp_cond(cat[t,text])) = [scale|shift]; NULL = no FiLM */
+  float *head_out;             /* [V*N,128]: type logits 0..103, coords 104..106 */
+  float *lattice_out;          /* [V*B,9] (may be NULL with coords_only) */
+  float *node_features;        /* [V*N,512] after final LN (may be NULL) */
+  int32_t coords_only;         /* corrector call: lattice head skipped */
+  int32_t precision;           /* cb2_precision */
+} cb2_forward_io;
+
+/* ---- sampler state + one reverse-diffusion timestep (chemeleon.py:379-467) ---- */
+typedef struct {
+  int64_t *atom_types;         /* [N] a_t  -> a_{t-1} (in place) */
+  float *frac_coords;          /* [N,3] x_t -> x_{t-1} (wrapped) */
+  float *lattices;             /* [B,9] l_t -> l_{t-1} */
+  int32_t *t_dev;              /* device scalar: current timestep; decremented by the step */
+  int32_t *flags;              /* [B] non-finite guard, 1 = crystal produced NaN/Inf */
+} cb2_state;
+
+typedef struct {
+  const float *coef;           /* [T+1,16] coefficient table (schedules.py) */
+  const float *text_part;      /* [V*B,1024] W_cond[:,128:] @ text + b  (cond rows then null rows) */
+  float cond_scale;
+  int32_t precision;
+  int32_t noise_mode;          /* 0 = injected tensors below, 1 = in-kernel Philox */
+  /* injected noise, indexed by step s = t_start - t: (chemeleon.py:400-404,418,435,455) */
+  int32_t t_start;             /* timestep of slice 0 of the injected tensors */
+  const float *rand_a;         /* [S,N,104] uniform */
+  const float *rand_l;         /* [S,B,9]   normal */
+  const float *rand_x;         /* [S,N,3]   normal, predictor */
+  const float *rand_x2;        /* [S,N,3]   normal, corrector */
+  /* Philox: noise keyed by (seed, global sample id, atom, timestep, stream) */
+  uint64_t seed;
+  const int64_t *graph_gid;    /* [B] global sample ids (sharding-invariant noise) */
+} cb2_step_args;
+
+/* Library / device checks. */
+int cb2_abi_version(void);
+const char *cb2_last_error(void);
+int cb2_check_device(int device);            /* CB2_OK iff compute capability 10.x */
+
+/* Workspace one forward / step needs for this batch (bytes). */
+size_t cb2_workspace_bytes(const cb2_batch *batch, int precision);
+
+/* h = node_embedding(atom_types); replaces cspnet.py:357 (also used by tests). */
+int cb2_embed_nodes(const cb2_model *m, const cb2_batch *b, const int64_t *atom_types,
+                    float *h /*[V*N,512]*/, void *stream);
+
+/* cond = SiLU(time_table[t] + text_part): FilmLayer.mlp_cond (cspnet.py:70-73,80-81)
+ * with the time half tabulated.  t is read from *t_dev. */
+int cb2_film_cond(const cb2_model *m, const cb2_batch *b, const float *text_part,
+                  const int32_t *t_dev, float *film_cond /*[V*B,1024]*/, void *stream);
+
+/* C = act(A W^T + bias): the fp32 linear the exact path is built from (tests). */
+int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bias, float *C,
+                   int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t silu, void *stream);
+
+/* One CSPNet.forward (cspnet.py:345-405) for all V variants of the batch. */
+int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* Predictor half of the update: CFG mix (chemeleon.py:288-290), D3PM.p_logits
+ * (diff_utils.py:307-329), lattice DDPM step (chemeleon.py:413-425), coordinate
+ * predictor (chemeleon.py:427-437).  x_t -> x_{t-1/2} (unwrapped) in place. */
+int cb2_update_predictor(const cb2_batch *b, cb2_state *s, const cb2_step_args *a,
+                         const float *head_out, const float *lattice_out, void *stream);
+
+/* Corrector half: Langevin step + mod-1 wrap (chemeleon.py:452-463); decrements *t_dev. */
+int cb2_update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a,
+                         const float *head_out, void *stream);
+
+/* One full timestep of Chemeleon._sample_generator's loop body (chemeleon.py:379-467):
+ * film_cond, predictor forward (cond+null), predictor update, corrector forward,
+ * corrector update.  Capturable in a CUDA graph; replay T times. */
+int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const cb2_step_args *a,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernels launched by this library in this process (bench: gpu_launches). */
+uint64_t cb2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEMELEON_B200_H */

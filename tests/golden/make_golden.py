@@ -1,0 +1,120 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so these
+fixtures are outputs of the reference's own `Chemeleon._sample_generator`
+(chemeleon/modules/chemeleon.py:305-467), imported through `oracle/ref_shim.py`,
+with
+  * weights  = chemeleon_b200.weights.random_init_state_dict(seed, head_scale)
+               loaded into the reference module (checkpoints are absent offline),
+  * text     = seeded synthetic cond / null embeddings (the BERT encoder is off
+               the hot path and not downloadable),
+  * noise    = the reference's own CPU RNG after torch.manual_seed(noise_seed).
+Only seeds, small tensors and checksums are stored; the weights are regenerated
+from the seed by the tests and verified against the stored checksum.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_shim  # noqa: E402
+from chemeleon_b200.config import SamplerConfig  # noqa: E402
+from chemeleon_b200.weights import random_init_state_dict  # noqa: E402
+
+
+def weight_checksum(sd):
+    keys = sorted(k for k in sd if k.startswith("decoder."))
+    s = sum(float(sd[k].double().sum()) for k in keys)
+    a = sum(float(sd[k].double().abs().sum()) for k in keys)
+    return np.array([s, a], dtype=np.float64)
+
+
+def run_case(name, natoms, weight_seed, head_scale, noise_seed, text_seed, n_steps, record_ts, state_ts,
+             cond_scale=2.0, step_lr=1e-5):
+    ref = ref_shim.load_reference()
+    model = ref_shim.build_reference_model(0)
+    cfg = SamplerConfig()
+    sd = random_init_state_dict(cfg, seed=weight_seed, head_scale=head_scale)
+    res = model.load_state_dict(sd, strict=False)
+    assert not [k for k in res.missing_keys if k.startswith(("decoder.", "sigma_scheduler."))], res
+    B, N = len(natoms), sum(natoms)
+    g = torch.Generator().manual_seed(text_seed)
+    text = torch.randn(B, cfg.text_dim, generator=g)
+    null = torch.randn(1, cfg.text_dim, generator=g)
+    model.text_encoder.cond = text
+    model.text_encoder.null = null
+
+    states = {}
+    Orig = ref.schema.TrajectoryContainer
+
+    class Recording(Orig):
+        def __setitem__(self, t, step):
+            states[t] = (step.atom_types.clone(), step.frac_coords.clone(), step.lattices.clone())
+            super().__setitem__(t, step)
+
+    ref.chemeleon.TrajectoryContainer = Recording
+    preds = []
+    orig_mp = model.model_predictions
+
+    def recording_mp(*a, **k):
+        out = orig_mp(*a, **k)
+        preds.append(tuple(o.clone() for o in out))
+        return out
+
+    model.model_predictions = recording_mp
+    torch.manual_seed(noise_seed)
+    gen = model._sample_generator(list(natoms), ["synthetic prompt"] * B, cond_scale, step_lr)
+    T = cfg.timesteps
+    for k, _ in enumerate(gen):
+        if k + 1 == n_steps:
+            break
+    ref.chemeleon.TrajectoryContainer = Orig
+
+    out = dict(
+        natoms=np.array(natoms, dtype=np.int64), weight_seed=np.int64(weight_seed),
+        head_scale=np.float64(head_scale), noise_seed=np.int64(noise_seed),
+        cond_scale=np.float64(cond_scale), step_lr=np.float64(step_lr), n_steps=np.int64(n_steps),
+        text=text.numpy(), null_text=null.numpy(), weight_checksum=weight_checksum(sd),
+        sigmas_norm=sd["sigma_scheduler.sigmas_norm"].numpy(),
+        record_ts=np.array(record_ts, dtype=np.int64), state_ts=np.array(state_ts, dtype=np.int64))
+    for t in state_ts:
+        a, x, l = states[t]
+        out[f"state{t}_a"], out[f"state{t}_x"], out[f"state{t}_l"] = a.numpy(), x.numpy(), l.numpy()
+    for t in record_ts:
+        k = T - t  # iteration index
+        pa, pl, px = preds[2 * k]
+        _, _, px2 = preds[2 * k + 1]
+        a, x, l = states[t]
+        an, xn, ln = states[t - 1]
+        out[f"rec{t}_a_t"], out[f"rec{t}_x_t"], out[f"rec{t}_l_t"] = a.numpy(), x.numpy(), l.numpy()
+        out[f"rec{t}_pred_a"], out[f"rec{t}_pred_l"], out[f"rec{t}_pred_x"] = pa.numpy(), pl.numpy(), px.numpy()
+        out[f"rec{t}_pred_x2"] = px2.numpy()
+        out[f"rec{t}_a_next"], out[f"rec{t}_x_next"], out[f"rec{t}_l_next"] = an.numpy(), xn.numpy(), ln.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count() or 1)
+    T = 1000
+    # BASELINE config 1 (n_atoms=6, n_samples=3), full 1000 steps, tamed heads so the
+    # free-running trajectory stays bounded and the final structure is meaningful.
+    run_case("c1_tamed_1000", [6, 6, 6], weight_seed=0, head_scale=0.01, noise_seed=7, text_seed=1,
+             n_steps=1000, record_ts=[1000, 999, 500, 2, 1], state_ts=[1000, 999, 998, 970, 500, 30, 2, 1, 0])
+    # full-scale heads, first steps only (the dynamics blow up later with random weights)
+    run_case("c1_full_6", [6, 6, 6], weight_seed=0, head_scale=1.0, noise_seed=7, text_seed=1,
+             n_steps=6, record_ts=[1000, 999, 995], state_ts=[1000, 999, 998, 995, 994])
+    # ragged crystals (config 5 style)
+    run_case("ragged_full_4", [4, 7, 5, 1, 9], weight_seed=3, head_scale=1.0, noise_seed=9, text_seed=4,
+             n_steps=4, record_ts=[1000, 999, 997], state_ts=[1000, 999, 998, 997, 996])
