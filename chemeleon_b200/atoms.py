@@ -1,0 +1,89 @@
+"""Output boundary: device state -> list of `ase.Atoms`.
+
+Restates `TrajectoryContainer.get_atoms` (chemeleon/modules/schema.py:57-83):
+types > 103 -> 0, split per crystal, `Atoms(numbers, cell=lattice, pbc=True)`,
+`set_scaled_positions(frac)`, `ase.build.tools.sort(atoms)` (stable sort by
+chemical-symbol string).  If `ase` is not installed a minimal stand-in with the
+same attributes is returned.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+SYMBOLS = [
+    "X", "H", "He", "Li", "Be", "B", "C", "N", "O", "F", "Ne", "Na", "Mg", "Al", "Si", "P", "S", "Cl", "Ar",
+    "K", "Ca", "Sc", "Ti", "V", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn", "Ga", "Ge", "As", "Se", "Br", "Kr",
+    "Rb", "Sr", "Y", "Zr", "Nb", "Mo", "Tc", "Ru", "Rh", "Pd", "Ag", "Cd", "In", "Sn", "Sb", "Te", "I", "Xe",
+    "Cs", "Ba", "La", "Ce", "Pr", "Nd", "Pm", "Sm", "Eu", "Gd", "Tb", "Dy", "Ho", "Er", "Tm", "Yb", "Lu",
+    "Hf", "Ta", "W", "Re", "Os", "Ir", "Pt", "Au", "Hg", "Tl", "Pb", "Bi", "Po", "At", "Rn", "Fr", "Ra", "Ac",
+    "Th", "Pa", "U", "Np", "Pu", "Am", "Cm", "Bk", "Cf", "Es", "Fm", "Md", "No", "Lr",
+]
+
+try:  # pragma: no cover - ase is absent in the offline image
+    from ase import Atoms as _AseAtoms
+    from ase.build.tools import sort as _ase_sort
+
+    HAVE_ASE = True
+except Exception:  # pragma: no cover
+    HAVE_ASE = False
+
+
+class AtomsLite:
+    """Stand-in for ase.Atoms when ase is not importable."""
+
+    def __init__(self, numbers, cell, scaled_positions, pbc=True):
+        self.numbers = np.asarray(numbers, dtype=np.int64)
+        self.cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+        self._scaled = np.asarray(scaled_positions, dtype=np.float64).reshape(-1, 3)
+        self.pbc = np.array([pbc] * 3)
+
+    def get_scaled_positions(self):
+        return self._scaled
+
+    def get_atomic_numbers(self):
+        return self.numbers
+
+    def get_chemical_symbols(self):
+        return [SYMBOLS[z] for z in self.numbers]
+
+    def get_cell(self):
+        return self.cell
+
+    @property
+    def positions(self):
+        return self._scaled @ self.cell
+
+    def __len__(self):
+        return len(self.numbers)
+
+    def __repr__(self):
+        return f"AtomsLite(symbols={''.join(self.get_chemical_symbols())}, n={len(self)})"
+
+
+def symbol_sort_order(numbers: np.ndarray) -> np.ndarray:
+    """Index order of `ase.build.tools.sort`: sorted((symbol, index))."""
+    deco = sorted((SYMBOLS[int(z)], i) for i, z in enumerate(numbers))
+    return np.array([i for _, i in deco], dtype=np.int64)
+
+
+def state_to_atoms(atom_types: np.ndarray, frac_coords: np.ndarray, lattices: np.ndarray,
+                   natoms: Sequence[int]) -> List:
+    a = np.where(atom_types <= 103, atom_types, 0)
+    a = np.where(a >= 0, a, 0)
+    out = []
+    off = 0
+    lat = lattices.reshape(-1, 3, 3)
+    for i, n in enumerate(natoms):
+        z = a[off:off + n]
+        pos = frac_coords[off:off + n]
+        off += n
+        if HAVE_ASE:  # pragma: no cover
+            at = _AseAtoms(numbers=z, cell=lat[i], pbc=True)
+            at.set_scaled_positions(pos)
+            out.append(_ase_sort(at))
+        else:
+            order = symbol_sort_order(z)
+            out.append(AtomsLite(z[order], lat[i], pos[order]))
+    return out

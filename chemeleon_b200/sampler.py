@@ -1,0 +1,309 @@
+"""`ChemeleonB200`: the reverse-diffusion sampler behind the reference's API.
+
+Mirrors `Chemeleon.sample(text_input, n_atoms, n_samples, cond_scale=2.0,
+step_lr=1e-5, return_trajectory=False, stream=False)` and the ragged
+`_sample_generator(natoms, texts, cond_scale, step_lr)`
+(chemeleon/modules/chemeleon.py:469-490, 305-467).  One timestep = one call of
+`cb2_sampler_step` (film cond, predictor forward cond|null, predictor update,
+corrector forward, corrector update), captured once in a CUDA graph and replayed
+T times with a device-side timestep counter; nothing crosses the host/device
+boundary inside the loop unless the caller asks for the per-step stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib, schedules
+from .atoms import state_to_atoms
+from .config import SamplerConfig
+from .engine import DecoderEngine, _stream_ptr
+from .topology import BatchTopology
+
+LATTICE_MASK = [[1, 0, 1], [1, 1, 1], [0, 0, 1]]  # chemeleon.py:70-72
+
+
+class InjectedNoise:
+    """Noise tensors in the reference's draw order (chemeleon.py:347-349,400-404,418,435,455).
+
+    l_T [B,3,3], x_T [N,3]; rand_a [S,N,104], rand_l [S,B,3,3], rand_x / rand_x2 [S,N,3]
+    with slice s belonging to timestep t_start - s (zeros where t == 1)."""
+
+    def __init__(self, l_T, x_T, rand_a, rand_l, rand_x, rand_x2, t_start: int):
+        self.l_T, self.x_T = l_T, x_T
+        self.rand_a, self.rand_l, self.rand_x, self.rand_x2 = rand_a, rand_l, rand_x, rand_x2
+        self.t_start = int(t_start)
+
+
+class SamplerRun:
+    """Device buffers + (optionally captured) step for one batch on one GPU."""
+
+    def __init__(self, engine: DecoderEngine, natoms: Sequence[int], text: Optional[torch.Tensor],
+                 null_text: Optional[torch.Tensor], cond_scale: float, step_lr: float,
+                 noise: Optional[InjectedNoise] = None, seed: int = 0,
+                 graph_gid: Optional[Sequence[int]] = None, use_cuda_graph: bool = True):
+        self.eng = engine
+        cfg = engine.cfg
+        dev = engine.device
+        self.text_guide = text is not None
+        V = 2 if self.text_guide else 1
+        self.topo: BatchTopology = engine.topology(natoms, V)
+        B, N = self.topo.B, self.topo.N
+        self.B, self.N, self.V = B, N, V
+        self.T = cfg.timesteps
+        with torch.cuda.device(dev):
+            self.ws = engine.workspace(self.topo)
+            self.a = torch.zeros(N, dtype=torch.int64, device=dev)
+            self.x = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+            self.l = torch.zeros(B, 9, dtype=torch.float32, device=dev)
+            self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.flags = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
+            coef = schedules.coefficient_table(cfg.timesteps, engine.w.sigmas_norm, step_lr, cfg.sigma_begin,
+                                               cfg.sigma_end, cfg.beta_schedule, engine.w.q_mats,
+                                               engine.w.q_one_step_mats)
+            self.coef = coef.to(dev)
+            if self.text_guide:
+                text = text.to(dev, torch.float32)
+                null_text = null_text.to(dev, torch.float32)
+                if null_text.shape[0] == 1:
+                    null_text = null_text.expand(B, -1)
+                if text.shape[0] != B or null_text.shape[0] != B:
+                    raise ValueError("text embeddings must have one row per crystal")
+                self.text_part = engine.text_part(torch.cat([text, null_text], dim=0))
+            else:
+                self.text_part = engine.w.film_b_cond.unsqueeze(0).expand(B, -1).contiguous()
+            gid = np.arange(B, dtype=np.int64) if graph_gid is None else np.asarray(graph_gid, dtype=np.int64)
+            self.graph_gid = torch.from_numpy(gid).to(dev)
+        self.noise = noise
+        if noise is not None:
+            self._noise_dev = [t.to(dev, torch.float32).contiguous() for t in
+                               (noise.rand_a, noise.rand_l.reshape(noise.rand_l.shape[0], -1, 9), noise.rand_x,
+                                noise.rand_x2)]
+        self.state = _lib.State()
+        self.state.atom_types, self.state.frac_coords = self.a.data_ptr(), self.x.data_ptr()
+        self.state.lattices, self.state.t_dev, self.state.flags = (self.l.data_ptr(), self.t_dev.data_ptr(),
+                                                                  self.flags.data_ptr())
+        args = _lib.StepArgs()
+        args.coef, args.text_part = self.coef.data_ptr(), self.text_part.data_ptr()
+        args.cond_scale = float(cond_scale)
+        args.timesteps = cfg.timesteps
+        args.precision = engine.precision
+        if noise is not None:
+            args.noise_mode, args.t_start = 0, noise.t_start
+            args.rand_a, args.rand_l, args.rand_x, args.rand_x2 = [t.data_ptr() for t in self._noise_dev]
+        else:
+            args.noise_mode, args.t_start = 1, cfg.timesteps
+        args.seed = int(seed) & (2 ** 64 - 1)
+        args.graph_gid = self.graph_gid.data_ptr()
+        self.args = args
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+
+    # -- state ---------------------------------------------------------------
+    def set_state(self, a: torch.Tensor, x: torch.Tensor, l: torch.Tensor, t: int) -> None:
+        dev = self.eng.device
+        self.a.copy_(a.to(dev, torch.int64))
+        self.x.copy_(x.to(dev, torch.float32))
+        self.l.copy_(l.to(dev, torch.float32).reshape(-1, 9))
+        self.t_dev.fill_(int(t))
+        self.flags.zero_()
+
+    def init_state(self, l_T: torch.Tensor, x_T: torch.Tensor, t_start: Optional[int] = None) -> None:
+        """a_T = 0, l_T masked, x_T wrapped (chemeleon.py:347-361)."""
+        dev = self.eng.device
+        mask = torch.tensor(LATTICE_MASK, dtype=torch.float32, device=dev)
+        l = l_T.to(dev, torch.float32).reshape(-1, 3, 3) * mask
+        x = torch.remainder(x_T.to(dev, torch.float32), 1.0)
+        self.set_state(torch.zeros(self.N, dtype=torch.int64, device=dev), x, l,
+                       self.T if t_start is None else t_start)
+
+    def get_state(self):
+        return self.a.clone(), self.x.clone(), self.l.clone().view(-1, 3, 3)
+
+    # -- stepping --------------------------------------------------------------
+    def _step_eager(self) -> None:
+        _lib.check(self.eng.lib.cb2_sampler_step(C.byref(self.eng.model), self.topo.byref(), C.byref(self.state),
+                                                 C.byref(self.args), self.ws.data_ptr(), self.ws.numel(),
+                                                 _stream_ptr()), "cb2_sampler_step")
+
+    def capture(self) -> None:
+        """Warm up once (module load), restore the state, then capture one timestep."""
+        if self._graph is not None or not self.use_cuda_graph:
+            return
+        saved = (self.a.clone(), self.x.clone(), self.l.clone(), self.t_dev.clone(), self.flags.clone())
+        if int(saved[3].item()) < 1:
+            self.t_dev.fill_(1)
+        s = torch.cuda.Stream(device=self.eng.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.eng.device)
+        for dst, src in zip((self.a, self.x, self.l, self.t_dev, self.flags), saved):
+            dst.copy_(src)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self._step_eager()
+        for dst, src in zip((self.a, self.x, self.l, self.t_dev, self.flags), saved):
+            dst.copy_(src)
+        self._graph = g
+
+    def step(self) -> None:
+        if self.use_cuda_graph:
+            if self._graph is None:
+                self.capture()
+            self._graph.replay()
+        else:
+            self._step_eager()
+
+    def run(self, n_steps: int) -> None:
+        for _ in range(n_steps):
+            self.step()
+
+
+class ChemeleonB200:
+    """B200 sampler with the reference `Chemeleon` sampling API."""
+
+    def __init__(self, source, cfg: Optional[SamplerConfig] = None, text_encoder=None, device="cuda",
+                 precision: str = "fp32", use_cuda_graph: bool = True):
+        """`source`: reference `Chemeleon` module, state_dict or checkpoint dict.
+        `text_encoder`: object with the reference `TextEncoder.get_text_embeds(texts, cond_drop_prob, device)`
+        interface (chemeleon/text_encoder/text_encoder.py:186-205); only needed for string prompts."""
+        if cfg is None and hasattr(source, "hparams"):
+            cfg = SamplerConfig.from_hparams(source.hparams)
+        if text_encoder is None and hasattr(source, "text_encoder"):
+            text_encoder = source.text_encoder
+        self.cfg = cfg or SamplerConfig()
+        self.engine = DecoderEngine(source, self.cfg, device, precision)
+        self.device = self.engine.device
+        self.text_encoder = text_encoder
+        self.text_guide = self.cfg.text_guide
+        self.use_cuda_graph = use_cuda_graph
+        self.hparams = self.cfg
+
+    # -- loaders (reference: chemeleon.py:97-135) ----------------------------------
+    @classmethod
+    def load_from_checkpoint(cls, path_ckpt: str, text_encoder=None, **kw) -> "ChemeleonB200":
+        if not os.path.exists(path_ckpt):
+            raise FileNotFoundError(f"{path_ckpt}: checkpoints are not bundled and cannot be downloaded offline")
+        ckpt = torch.load(path_ckpt, map_location="cpu", weights_only=False)
+        cfg = SamplerConfig.from_hparams(ckpt.get("hyper_parameters", {}))
+        return cls(ckpt["state_dict"], cfg, text_encoder=text_encoder, **kw)
+
+    @classmethod
+    def load_general_text_model(cls, checkpoint_dir: Optional[str] = None, **kw) -> "ChemeleonB200":
+        d = checkpoint_dir or os.environ.get("CHEMELEON_CHECKPOINT_DIR", "checkpoints")
+        return cls.load_from_checkpoint(os.path.join(d, "chemeleon-7fsg68c3.ckpt"), **kw)
+
+    @classmethod
+    def load_composition_model(cls, checkpoint_dir: Optional[str] = None, **kw) -> "ChemeleonB200":
+        d = checkpoint_dir or os.environ.get("CHEMELEON_CHECKPOINT_DIR", "checkpoints")
+        return cls.load_from_checkpoint(os.path.join(d, "chemeleon-fksq6cgp.ckpt"), **kw)
+
+    def eval(self):
+        return self
+
+    # -- text ------------------------------------------------------------------
+    def _embed_texts(self, texts: Sequence[str]):
+        if self.text_encoder is None:
+            raise ValueError("string prompts need a text_encoder; pass text_embeds/null_text_embeds instead")
+        te = self.text_encoder.get_text_embeds(list(texts), cond_drop_prob=0.0, device=self.device)
+        ne = self.text_encoder.get_text_embeds(list(texts), cond_drop_prob=1.0, device=self.device)
+        return te.detach(), ne.detach()
+
+    # -- core ------------------------------------------------------------------
+    def make_run(self, natoms: Sequence[int], text_embeds=None, null_text_embeds=None, cond_scale: float = 2.0,
+                 step_lr: float = 1e-5, noise: Optional[InjectedNoise] = None, seed: int = 0,
+                 graph_gid=None) -> SamplerRun:
+        if self.text_guide and text_embeds is None:
+            raise ValueError("text_guide model: text embeddings are required")
+        if not self.text_guide:
+            text_embeds = null_text_embeds = None
+        return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed,
+                          graph_gid, self.use_cuda_graph)
+
+    def initial_noise(self, B: int, N: int, seed: int):
+        """l_T, x_T from a device generator (production mode; global order => sharding invariant)."""
+        g = torch.Generator(device=self.device).manual_seed(int(seed))
+        l_T = torch.randn(B, 3, 3, generator=g, device=self.device)
+        x_T = torch.randn(N, 3, generator=g, device=self.device)
+        return l_T, x_T
+
+    @torch.no_grad()
+    def sample_states(self, natoms: Sequence[int], text_embeds=None, null_text_embeds=None,
+                      cond_scale: float = 2.0, step_lr: float = 1e-5, noise: Optional[InjectedNoise] = None,
+                      seed: int = 0, t_stop: int = 0, init_state=None, t_start: Optional[int] = None,
+                      per_step: Optional[Callable] = None, graph_gid=None, init_noise=None):
+        """Run t = t_start .. t_stop+1 and return the device state (a, x, l) at t_stop."""
+        natoms = [int(n) for n in natoms]
+        with torch.cuda.device(self.device):
+            run = self.make_run(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed, graph_gid)
+            t0 = self.cfg.timesteps if t_start is None else int(t_start)
+            if init_state is not None:
+                run.set_state(*init_state, t0)
+            else:
+                if noise is not None:
+                    l_T, x_T = noise.l_T, noise.x_T
+                elif init_noise is not None:
+                    l_T, x_T = init_noise
+                else:
+                    l_T, x_T = self.initial_noise(run.B, run.N, seed)
+                run.init_state(l_T, x_T, t0)
+            for t in range(t0, t_stop, -1):
+                run.step()
+                if per_step is not None:
+                    per_step(t - 1, run)
+            a, x, l = run.get_state()
+            self.last_flags = run.flags.clone()
+        return a, x, l
+
+    def _to_atoms(self, a, x, l, natoms):
+        return state_to_atoms(a.cpu().numpy(), x.cpu().numpy(), l.reshape(-1, 9).cpu().numpy(), natoms)
+
+    # -- reference API ---------------------------------------------------------------
+    def _sample_generator(self, natoms: Union[int, List[int]], texts: Optional[Union[str, List[str]]] = None,
+                          cond_scale: float = 2.0, step_lr: float = 1e-5, *, text_embeds=None,
+                          null_text_embeds=None, noise=None, seed: int = 0) -> Iterator[List]:
+        """Yields `List[Atoms]` once per timestep (T items), like the reference generator."""
+        if isinstance(natoms, int):
+            natoms = [natoms]
+        if isinstance(texts, str):
+            texts = [texts]
+        if texts is not None and len(texts) != len(natoms):
+            raise ValueError("natoms and texts must have the same number of elements.")
+        if self.text_guide and text_embeds is None:
+            text_embeds, null_text_embeds = self._embed_texts(texts)
+        natoms = [int(n) for n in natoms]
+        with torch.cuda.device(self.device):
+            run = self.make_run(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed)
+            if noise is not None:
+                run.init_state(noise.l_T, noise.x_T)
+            else:
+                run.init_state(*self.initial_noise(run.B, run.N, seed))
+            for _t in range(self.cfg.timesteps, 0, -1):
+                run.step()
+                yield self._to_atoms(run.a, run.x, run.l, natoms)
+
+    def sample(self, text_input: str, n_atoms: int, n_samples: int, cond_scale: float = 2.0,
+               step_lr: float = 1e-5, return_trajectory: bool = False, stream: bool = False, **kw):
+        natoms = [n_atoms] * n_samples
+        texts = [text_input] * n_samples
+        if stream:
+            return self._sample_generator(natoms, texts, cond_scale, step_lr, **kw)
+        if return_trajectory:
+            return list(self._sample_generator(natoms, texts, cond_scale, step_lr, **kw))
+        return self.sample_batch(natoms, texts, cond_scale=cond_scale, step_lr=step_lr, **kw)
+
+    def sample_batch(self, natoms: Sequence[int], texts: Optional[Sequence[str]] = None, *, text_embeds=None,
+                     null_text_embeds=None, cond_scale: float = 2.0, step_lr: float = 1e-5, noise=None,
+                     seed: int = 0):
+        """Ragged entry point (the use-case of the reference's stale list-based callers,
+        scripts/evaluate.py:97-99): final structures only, one D2H at the end."""
+        if self.text_guide and text_embeds is None:
+            text_embeds, null_text_embeds = self._embed_texts(texts)
+        a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed)
+        return self._to_atoms(a, x, l, [int(n) for n in natoms])

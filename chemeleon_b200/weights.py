@@ -240,4 +240,5 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
         final_b=d(get("decoder.final_layer_norm.bias")),
         w_head=d(w_head), b_head=d(b_head), w_head_t=tiled(w_head),
         w_lat=d(get("decoder.lattice_out.weight")), sigmas_norm=sn,
-        q_mats=sd.get("d3pm.q_mats"), q_one_step_mats=sd.get("d3pm.q_one_step_mats"))
+        q_mats=sd.get("d3pm.q_mats"), q_one_step_mats=sd.get("d3pm.q_one_step_mats"),
+        extra={"film_w_cond": d(w_cond)})

@@ -112,6 +112,7 @@ typedef struct {
   const int64_t *node_eoff;    /* [N+1] edge-row offset of node i's segment */
   int32_t n_chunks;            /* exact path processes edges in chunks of whole segments */
   const int32_t *host_chunk_node_lo; /* HOST [n_chunks+1] node boundaries of the chunks */
+  const int64_t *host_chunk_edge_lo; /* HOST [n_chunks+1] edge-row boundaries of the chunks */
   int64_t chunk_max_edges;     /* largest chunk, in edge rows */
   /* tensor-core path: tiles of 128 edge rows = whole segments of equal length */
   int32_t n_tiles;
@@ -146,6 +147,7 @@ typedef struct {
   const float *coef;           /* [T+1,16] coefficient table (schedules.py) */
   const float *text_part;      /* [V*B,1024] W_cond[:,128:] @ text + b  (cond rows then null rows) */
   float cond_scale;
+  int32_t timesteps;           /* T: the lattice is clipped to [-6,6] at t == T only (chemeleon.py:424-425) */
   int32_t precision;
   int32_t noise_mode;          /* 0 = injected tensors below, 1 = in-kernel Philox */
   /* injected noise, indexed by step s = t_start - t: (chemeleon.py:400-404,418,435,455) */

@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle
+and the committed golden fixtures of the unmodified reference.
+
+Tolerances (relative = max|a-b| / max|b|):
+  * fp32 exact mode: 1e-4 on decoder outputs (observed ~1e-6), types bit-exact on fixtures
+  * tensor-core mode (fp16 operands, fp32 accumulate): 1e-3, the north-star tolerance
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, golden_weights, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32"]
+TOL = {"fp32": 1e-4, "tc": 1e-3}
+
+
+def _tc_available():
+    import os
+
+    src = os.path.join(os.path.dirname(__file__), "..", "chemeleon_b200", "csrc", "cb2_tc.cu")
+    return "not built yet" not in open(src).read()
+
+
+if _tc_available():
+    PRECISIONS.append("tc")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import chemeleon_oracle
+
+    return chemeleon_oracle
+
+
+@pytest.fixture(scope="module")
+def sd11():
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.weights import random_init_state_dict
+
+    return random_init_state_dict(SamplerConfig(), seed=11)
+
+
+def test_library_loads_on_device():
+    from chemeleon_b200 import _lib
+
+    lib = _lib.load()
+    _lib.check(lib.cb2_check_device(0), "cb2_check_device")
+
+
+def test_linear_f32_matches_torch():
+    from chemeleon_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K, silu) in [(1, 512, 512, 0), (130, 1024, 512, 1), (257, 128, 512, 0), (64, 512, 768, 1)]:
+        A = torch.randn(M, K, generator=g)
+        W = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g)
+        ref = torch.nn.functional.linear(A.double(), W.double(), b.double())
+        if silu:
+            ref = torch.nn.functional.silu(ref)
+        Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+        Cd = torch.empty(M, N, device="cuda")
+        _lib.check(lib.cb2_linear_f32(Ad.data_ptr(), K, Wd.data_ptr(), bd.data_ptr(), Cd.data_ptr(), N, M, N, K,
+                                      silu, torch.cuda.current_stream().cuda_stream), "linear")
+        assert rel_err(Cd.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("natoms", [[4, 7, 5, 1], [20] * 7, [40, 3, 33], [1], [6, 6, 6]])
+def test_decoder_forward_vs_oracle(O, sd11, precision, natoms):
+    """CSPNetB200.forward == oracle cspnet_forward (== reference CSPNet.forward)."""
+    from chemeleon_b200.cspnet import CSPNetB200
+
+    net = CSPNetB200(sd11, precision=precision)
+    nat = torch.tensor(natoms)
+    B, N = len(natoms), sum(natoms)
+    bi = torch.arange(B).repeat_interleave(nat)
+    g = torch.Generator().manual_seed(3)
+    a = torch.randint(0, 104, (N,), generator=g)
+    x = torch.rand(N, 3, generator=g) * 3 - 1  # unwrapped coordinates are legal decoder input
+    l = torch.randn(B, 3, 3, generator=g)
+    temb = O.time_embedding(torch.randint(1, 1001, (B,), generator=g), 128)
+    text = torch.randn(B, 512, generator=g)
+    w = {k: v for k, v in sd11.items() if k.startswith("decoder.")}
+    ref = O.cspnet_forward(w, a, x, l, nat, bi, temb, text)
+    out = net(a, x, l, nat, bi, t=temb, text_embeds=text)
+    tol = TOL[precision]
+    for name, r, o in zip(("types", "lattice", "coords", "features"), ref, out):
+        assert rel_err(o.cpu(), r) < tol, name
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_decoder_forward_without_film(O, sd11, precision):
+    """t=None, text_embeds=None skips FiLM (CrystalClip's use, cspnet.py:372)."""
+    from chemeleon_b200.cspnet import CSPNetB200
+
+    net = CSPNetB200(sd11, precision=precision)
+    natoms = [5, 9]
+    nat = torch.tensor(natoms)
+    bi = torch.arange(2).repeat_interleave(nat)
+    g = torch.Generator().manual_seed(4)
+    a = torch.randint(0, 104, (14,), generator=g)
+    x = torch.rand(14, 3, generator=g)
+    l = torch.randn(2, 3, 3, generator=g)
+    w = {k: v for k, v in sd11.items() if k.startswith("decoder.")}
+    ref = O.cspnet_forward(w, a, x, l, nat, bi, None, None)
+    out = net(a, x, l, nat, bi)
+    for r, o in zip(ref, out):
+        assert rel_err(o.cpu(), r) < TOL[precision]
+
+
+def _structs_for_update(natoms, V, a, x, l, coef, t, cond_scale, noise4, T=1000):
+    from chemeleon_b200 import _lib
+    from chemeleon_b200.topology import BatchTopology
+
+    topo = BatchTopology(natoms, V, "cuda", exact=False, tensor_core=False)
+    st = _lib.State()
+    t_dev = torch.tensor([t], dtype=torch.int32, device="cuda")
+    flags = torch.zeros(len(natoms), dtype=torch.int32, device="cuda")
+    st.atom_types, st.frac_coords, st.lattices = a.data_ptr(), x.data_ptr(), l.data_ptr()
+    st.t_dev, st.flags = t_dev.data_ptr(), flags.data_ptr()
+    args = _lib.StepArgs()
+    args.coef = coef.data_ptr()
+    args.cond_scale = cond_scale
+    args.timesteps = T
+    args.noise_mode, args.t_start = 0, t
+    args.rand_a, args.rand_l, args.rand_x, args.rand_x2 = [n.data_ptr() for n in noise4]
+    keep = (topo, t_dev, flags)
+    return topo, st, args, keep
+
+
+@pytest.mark.parametrize("t", [1000, 637, 2, 1])
+def test_update_kernels_vs_oracle(O, t):
+    """cb2_update_predictor / cb2_update_corrector == chemeleon.py:400-463 + D3PM.p_logits."""
+    from chemeleon_b200 import _lib, schedules
+
+    lib = _lib.load()
+    natoms = [6, 3, 11]
+    B, N, V = 3, 20, 2
+    g = torch.Generator().manual_seed(100 + t)
+    head = torch.zeros(V * N, 128)
+    head[:, :107] = torch.randn(V * N, 107, generator=g) * 2
+    lat_out = torch.randn(V * B, 9, generator=g)
+    a = torch.randint(0, 104, (N,), generator=g)
+    a[::4] = 0
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g) * 3
+    sn = torch.cat([torch.ones(1), torch.rand(1000, generator=g) + 0.5])
+    ra = torch.rand(1, N, 104, generator=g)
+    rl = torch.randn(1, B, 9, generator=g)
+    rx = torch.randn(1, N, 3, generator=g)
+    rx2 = torch.randn(1, N, 3, generator=g)
+    if t == 1:
+        ra, rl, rx, rx2 = [torch.zeros_like(v) for v in (ra, rl, rx, rx2)]
+    cs, step_lr = 2.0, 1e-5
+    # ---- oracle, following chemeleon.py line by line ----
+    so_beta, so_sig = O.beta_tables(1000), O.sigma_tables(1000)
+    tab = O.D3PMTables(so_beta["betas"])
+    pa = (1 - cs) * head[N:, :104] + cs * head[:N, :104]
+    px = (1 - cs) * head[N:, 104:107] + cs * head[:N, 104:107]
+    pl = ((1 - cs) * lat_out[B:] + cs * lat_out[:B]).view(B, 3, 3)
+    bi = torch.arange(B).repeat_interleave(torch.tensor(natoms))
+    a_ref = O.d3pm_p_logits(tab, pa, a, torch.full((N,), t), ra[0])
+    mask = O.LATTICE_MASK
+    al, ac, sg = so_beta["alphas"][t], so_beta["alphas_cumprod"][t], so_beta["sigmas"][t]
+    l_ref = (1.0 / torch.sqrt(al)) * (l - ((1 - al) / torch.sqrt(1 - ac)) * pl) + sg * (rl[0].view(B, 3, 3) * mask)
+    l_ref = l_ref * mask
+    if t == 1000:
+        l_ref = l_ref.clip(-6, 6)
+    sx, sxa = so_sig[t], so_sig[t - 1]
+    xh_ref = x - (sx ** 2 - sxa ** 2) * (px * torch.sqrt(sn[t])) + torch.sqrt(
+        (sxa ** 2 * (sx ** 2 - sxa ** 2)) / sx ** 2) * rx[0]
+    # ---- CUDA ----
+    coef = schedules.coefficient_table(1000, sn, step_lr).cuda()
+    ad, xd, ld = a.cuda(), x.cuda().contiguous(), l.reshape(B, 9).cuda().contiguous()
+    noise4 = [v.cuda().contiguous() for v in (ra, rl, rx, rx2)]
+    topo, st, args, keep = _structs_for_update(natoms, V, ad, xd, ld, coef, t, cs, noise4)
+    hd, lod = head.cuda(), lat_out.cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cb2_update_predictor(topo.byref(), C.byref(st), C.byref(args), hd.data_ptr(), lod.data_ptr(), s),
+               "predictor")
+    torch.cuda.synchronize()
+    assert torch.equal(ad.cpu(), a_ref), f"{(ad.cpu() != a_ref).sum()} type mismatches"
+    assert rel_err(ld.cpu().view(B, 3, 3), l_ref) < 1e-6
+    assert (xd.cpu() - xh_ref).abs().max() < 1e-6
+    # corrector on new head values
+    head2 = torch.zeros(V * N, 128)
+    head2[:, 104:107] = torch.randn(V * N, 3, generator=g)
+    px2 = (1 - cs) * head2[N:, 104:107] + cs * head2[:N, 104:107]
+    step2 = step_lr * (sx / 0.01) ** 2
+    xn_ref = (xh_ref - step2 * (px2 * torch.sqrt(sn[t])) + torch.sqrt(2 * step2) * rx2[0]) % 1.0
+    h2d = head2.cuda()
+    _lib.check(lib.cb2_update_corrector(topo.byref(), C.byref(st), C.byref(args), h2d.data_ptr(), s), "corrector")
+    torch.cuda.synchronize()
+    d = ((xd.cpu() - xn_ref + 0.5) % 1.0 - 0.5).abs().max()
+    assert d < 1e-6
+    assert int(keep[1].item()) == t - 1  # device-side timestep counter advanced
+
+
+def _golden_noise(O, g, t_hi, t_lo):
+    natoms = g["natoms"].tolist()
+    rn = O.ReferenceNoise(int(g["noise_seed"]), len(natoms), sum(natoms))
+    if t_hi < 1000:
+        rn.materialize(1000, t_hi + 1)  # replay the RNG stream up to t_hi
+    return rn, rn.materialize(t_hi, t_lo)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_golden_teacher_forced_steps(O, precision, case):
+    """One cb2_sampler_step from the reference's recorded state at t reproduces the
+    reference's state at t-1 (fixtures generated from the unmodified reference)."""
+    from chemeleon_b200.sampler import ChemeleonB200, InjectedNoise
+
+    g = load_golden(case)
+    sd = golden_weights(g)
+    model = ChemeleonB200(sd, precision=precision, use_cuda_graph=False)
+    natoms = g["natoms"].tolist()
+    text, null = torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"])
+    tol = TOL[precision]
+    for t in [int(v) for v in g["record_ts"]]:
+        rn, (ra, rl, rx, rx2) = _golden_noise(O, g, t, t)
+        noise = InjectedNoise(rn.l_T, rn.x_T, ra, rl, rx, rx2, t_start=t)
+        init = (torch.from_numpy(g[f"rec{t}_a_t"]), torch.from_numpy(g[f"rec{t}_x_t"]),
+                torch.from_numpy(g[f"rec{t}_l_t"]))
+        a, x, l = model.sample_states(natoms, text, null, float(g["cond_scale"]), float(g["step_lr"]),
+                                      noise=noise, t_start=t, t_stop=t - 1, init_state=init)
+        a_ref = g[f"rec{t}_a_next"]
+        match = float((a.cpu().numpy() == a_ref).mean())
+        if precision == "fp32":
+            assert match == 1.0, f"t={t}: type mismatch"
+        else:
+            assert match >= 0.9, f"t={t}: type match {match}"
+        assert rel_err(l.cpu(), g[f"rec{t}_l_next"]) < tol, f"t={t} lattice"
+        d = np.abs((x.cpu().numpy() - g[f"rec{t}_x_next"] + 0.5) % 1.0 - 0.5).max()
+        assert d < tol, f"t={t} coords {d}"
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_golden_decoder_outputs(O, precision):
+    """pred_a / pred_l / pred_x (CFG-mixed decoder outputs) at the recorded steps: the
+    north-star per-step criterion, 1e-3 relative."""
+    from chemeleon_b200.cspnet import CSPNetB200
+
+    for case in GOLDEN_CASES:
+        g = load_golden(case)
+        sd = golden_weights(g)
+        net = CSPNetB200(sd, precision=precision)
+        natoms = g["natoms"].tolist()
+        nat = torch.tensor(natoms)
+        B = len(natoms)
+        bi = torch.arange(B).repeat_interleave(nat)
+        text, null = torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"]).expand(B, -1)
+        cs = float(g["cond_scale"])
+        for t in [int(v) for v in g["record_ts"]]:
+            a, x, l = (torch.from_numpy(g[f"rec{t}_{k}"]) for k in ("a_t", "x_t", "l_t"))
+            temb = O.time_embedding(torch.full((B,), t), 128)
+            oc = net(a, x, l, nat, bi, t=temb, text_embeds=text)
+            on = net(a, x, l, nat, bi, t=temb, text_embeds=null)
+            for name, idx in (("pred_a", 0), ("pred_l", 1), ("pred_x", 2)):
+                mix = (1 - cs) * on[idx].cpu() + cs * oc[idx].cpu()
+                assert rel_err(mix, g[f"rec{t}_{name}"]) < TOL[precision], (case, t, name)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_golden_free_running_1000_steps(O, precision):
+    """BASELINE config 1 (n_atoms=6, n_samples=3): the full 1000-step run with the
+    reference's own noise reproduces the reference's final structures (tamed heads)."""
+    from chemeleon_b200.sampler import ChemeleonB200, InjectedNoise
+
+    g = load_golden("c1_tamed_1000")
+    sd = golden_weights(g)
+    model = ChemeleonB200(sd, precision=precision, use_cuda_graph=True)
+    natoms = g["natoms"].tolist()
+    rn, (ra, rl, rx, rx2) = _golden_noise(O, g, 1000, 1)
+    noise = InjectedNoise(rn.l_T, rn.x_T, ra, rl, rx, rx2, t_start=1000)
+    a, x, l = model.sample_states(natoms, torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"]),
+                                  float(g["cond_scale"]), float(g["step_lr"]), noise=noise)
+    match = float((a.cpu().numpy() == g["state0_a"]).mean())
+    d = np.abs((x.cpu().numpy() - g["state0_x"] + 0.5) % 1.0 - 0.5).max()
+    el = rel_err(l.cpu(), g["state0_l"])
+    print(f"[{precision}] free-running 1000 steps: type match {match:.3f}, coord err {d:.2e}, lattice rel {el:.2e}")
+    if precision == "fp32":
+        assert match == 1.0 and d < 1e-3 and el < 1e-3
+    else:
+        assert match >= 0.8 and el < 2e-2
+
+
+def test_cuda_graph_equals_eager(O):
+    from chemeleon_b200.sampler import ChemeleonB200, InjectedNoise
+
+    g = load_golden("ragged_full_4")
+    sd = golden_weights(g)
+    natoms = g["natoms"].tolist()
+    res = []
+    for graph in (False, True):
+        rn, (ra, rl, rx, rx2) = _golden_noise(O, g, 1000, 997)
+        noise = InjectedNoise(rn.l_T, rn.x_T, ra, rl, rx, rx2, t_start=1000)
+        model = ChemeleonB200(sd, precision="fp32", use_cuda_graph=graph)
+        res.append(model.sample_states(natoms, torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"]),
+                                       noise=noise, t_stop=996))
+    for u, v in zip(*res):
+        assert torch.equal(u, v)
+    assert (res[0][0].cpu().numpy() == g["state996_a"]).all()
+
+
+def test_philox_mode_is_deterministic_and_sharding_invariant():
+    """Production noise: same seed -> same structures; a crystal's result does not depend
+    on its batch-mates (noise keyed by global sample id)."""
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.sampler import ChemeleonB200
+    from chemeleon_b200.weights import random_init_state_dict
+
+    sd = random_init_state_dict(SamplerConfig(), seed=2, head_scale=0.01)
+    model = ChemeleonB200(sd, precision="fp32")
+    natoms = [5, 8, 3, 6]
+    B, N = 4, sum(natoms)
+    g = torch.Generator().manual_seed(0)
+    text, null = torch.randn(B, 512, generator=g), torch.randn(1, 512, generator=g)
+    l_T, x_T = torch.randn(B, 3, 3, generator=g), torch.randn(N, 3, generator=g)
+    kw = dict(seed=42, t_stop=990, init_noise=(l_T, x_T))
+    full = model.sample_states(natoms, text, null, graph_gid=[0, 1, 2, 3], **kw)
+    again = model.sample_states(natoms, text, null, graph_gid=[0, 1, 2, 3], **kw)
+    for u, v in zip(full, again):
+        assert torch.equal(u, v)
+    # shard = crystals 2,3 alone
+    sub = model.sample_states(natoms[2:], text[2:], null, seed=42, t_stop=990, graph_gid=[2, 3],
+                              init_noise=(l_T[2:], x_T[13:]))
+    assert torch.equal(sub[0], full[0][13:])
+    assert torch.allclose(sub[1], full[1][13:], atol=1e-5)
+    assert torch.allclose(sub[2], full[2][2:], atol=1e-5, rtol=1e-5)
+    other = model.sample_states(natoms, text, null, seed=43, t_stop=990, graph_gid=[0, 1, 2, 3],
+                                init_noise=(l_T, x_T))
+    assert not torch.equal(other[1], full[1])
