@@ -86,6 +86,9 @@ EXPORTS = {
     "cb2_film_cond": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), vp, vp, vp, vp]),
     "cb2_linear_f32": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, vp]),
+    "cb2_linear_tc": (C.c_int, [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]),
+    "cb2_edge_layer": (C.c_int, [C.POINTER(Model), C.c_int32, C.POINTER(Batch), vp, vp, vp, C.c_int64, C.c_int32,
+                                 vp, C.c_size_t, vp]),
     "cb2_decoder_forward": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), C.POINTER(ForwardIO), vp,
                                       C.c_size_t, vp]),
     "cb2_update_predictor": (C.c_int, [C.POINTER(Batch), C.POINTER(State), C.POINTER(StepArgs), vp, vp, vp]),

@@ -41,6 +41,10 @@ int update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, c
 // tensor-core path (cb2_tc.cu)
 int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                       cudaStream_t st);
+int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
+                     int64_t ldc, int64_t M, int K, int silu, cudaStream_t st);
+int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
+                  int64_t ld_agg, int agg_col, cudaStream_t st);
 
 size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) {
   const size_t VN = (size_t)b->n_variants * b->n_nodes;
@@ -105,6 +109,31 @@ static int check_batch(const cb2_batch *b, int precision) {
   return CB2_OK;
 }
 
+// ---- exact-mode edge model of one layer: emb -> GEMM1(+P gather, SiLU) -> GEMM2 -> segment mean ----
+static int f32_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P,
+                          float *agg, int64_t ld_agg, ForwardWs &w, cudaStream_t st) {
+  const int N = b->n_nodes, V = b->n_variants;
+  for (int c = 0; c < b->n_chunks; c++) {
+    const int nlo = b->host_chunk_node_lo[c], nhi = b->host_chunk_node_lo[c + 1];
+    const int64_t e0 = b->host_chunk_edge_lo[c], e1 = b->host_chunk_edge_lo[c + 1];
+    const int64_t rows = e1 - e0;
+    if (rows <= 0) continue;
+    if (rows > b->chunk_max_edges) return fail(CB2_ERR_BAD_ARG, "chunk larger than chunk_max_edges");
+    CB2_TRY(launch_edge_embed(x, b->edge_i + e0, b->edge_j + e0, w.emb, rows, st));
+    for (int v = 0; v < V; v++) {
+      GemmEpilogue e1p;
+      e1p.P = P; e1p.ei = b->edge_i + e0; e1p.ej = b->edge_j + e0; e1p.prow_off = (int64_t)v * N;
+      e1p.silu = 1;
+      CB2_TRY(launch_sgemm_nt(w.emb, DIS, L.w_fd, w.a1, H, rows, H, DIS, e1p, st));
+      GemmEpilogue e2p;
+      e2p.bias = L.b2; e2p.silu = 1;
+      CB2_TRY(launch_sgemm_nt(w.a1, H, L.w2, w.e2, H, rows, H, H, e2p, st));
+      CB2_TRY(launch_segment_mean(w.e2, b->node_eoff, b->node_n, agg, ld_agg, nlo, nhi, e0, (int64_t)v * N, st));
+    }
+  }
+  return CB2_OK;
+}
+
 // ---- exact-mode layers -------------------------------------------------------
 static int f32_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                               cudaStream_t st) {
@@ -125,25 +154,7 @@ static int f32_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_
       e.gbias = w.cg; e.gidx = b->node2graph; e.gmod = N; e.gcols = H; e.gld = H;
       CB2_TRY(launch_sgemm_nt(w.cat, H2, L.w_hij, w.P, H2, VN, H2, H, e, st));
     }
-    for (int c = 0; c < b->n_chunks; c++) {
-      const int nlo = b->host_chunk_node_lo[c], nhi = b->host_chunk_node_lo[c + 1];
-      const int64_t e0 = b->host_chunk_edge_lo[c], e1 = b->host_chunk_edge_lo[c + 1];
-      const int64_t rows = e1 - e0;
-      if (rows <= 0) continue;
-      if (rows > b->chunk_max_edges) return fail(CB2_ERR_BAD_ARG, "chunk larger than chunk_max_edges");
-      CB2_TRY(launch_edge_embed(io->frac_coords, b->edge_i + e0, b->edge_j + e0, w.emb, rows, st));
-      for (int v = 0; v < V; v++) {
-        GemmEpilogue e1p;
-        e1p.P = w.P; e1p.ei = b->edge_i + e0; e1p.ej = b->edge_j + e0; e1p.prow_off = (int64_t)v * N;
-        e1p.silu = 1;
-        CB2_TRY(launch_sgemm_nt(w.emb, DIS, L.w_fd, w.a1, H, rows, H, DIS, e1p, st));
-        GemmEpilogue e2p;
-        e2p.bias = L.b2; e2p.silu = 1;
-        CB2_TRY(launch_sgemm_nt(w.a1, H, L.w2, w.e2, H, rows, H, H, e2p, st));
-        CB2_TRY(launch_segment_mean(w.e2, b->node_eoff, b->node_n, w.cat + H, H2, nlo, nhi, e0,
-                                    (int64_t)v * N, st));
-      }
-    }
+    CB2_TRY(f32_edge_layer(L, b, io->frac_coords, w.P, w.cat + H, H2, w, st));
     {
       GemmEpilogue e;
       e.bias = L.bn1; e.silu = 1;
@@ -236,6 +247,31 @@ int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bia
   e.bias = bias;
   e.silu = silu;
   return launch_sgemm_nt(A, lda, W, C, ldc, M, N, K, e, (cudaStream_t)stream);
+}
+
+int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
+                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream) {
+  if (!A16 || !Wt || !C) return fail(CB2_ERR_BAD_ARG, "linear_tc: null argument");
+  return tc_linear_simple(A16, lda, Wt, Nw, bias, C, ldc, M, K, silu, (cudaStream_t)stream);
+}
+
+int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
+                   const float *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   size_t workspace_bytes, void *stream) {
+  CB2_TRY(check_model(m));
+  CB2_TRY(check_batch(b, precision));
+  if (layer < 0 || layer >= m->n_layers) return fail(CB2_ERR_BAD_ARG, "edge_layer: bad layer index");
+  if (!frac_coords || !P || !agg) return fail(CB2_ERR_BAD_ARG, "edge_layer: null argument");
+  const cb2_layer_weights &L = m->layers[layer];
+  if (precision == CB2_PRECISION_FP32) {
+    Arena a(workspace, workspace_bytes, false);
+    ForwardWs fw;
+    carve_forward(a, b, precision, fw);
+    if (!workspace || !a.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
+    return f32_edge_layer(L, b, frac_coords, P, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
+  }
+  if (!L.w_fd_t || !L.w2_t) return fail(CB2_ERR_BAD_ARG, "edge_layer: fp16 operand images missing");
+  return tc_edge_layer(L, b, frac_coords, P, (__half *)agg, ld_agg, 0, (cudaStream_t)stream);
 }
 
 int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, void *workspace,

@@ -1,10 +1,577 @@
-// Tensor-core (tcgen05 / TMEM) path of the CSPNet decoder -- placeholder until the kernels land.
+// Tensor-core path of the CSPNet decoder: tcgen05.mma (kind::f16, fp16 operands,
+// fp32 accumulators in TMEM), weights streamed by bulk async copies (TMA unit) from
+// pre-tiled operand images, A operands built in shared memory by the CUDA cores.
+//
+//   k_tc_linear : C = epi(A16 W16^T)       node-level GEMMs (FiLM proj, hoisted
+//                                           [W_hi;W_hj], node MLP)        cspnet.py:86,161
+//   k_tc_edge   : fused CSPLayer edge model + scatter_mean, edges generated on the
+//                 fly from per-tile (i,j) rows                            cspnet.py:138-160
+//
+// Shared-memory operand layout everywhere: K-major, no swizzle, [K/8][rows][8 halves]
+// (core matrix = 8 rows x 16 B; SBO = 128 B, LBO = rows*16 B).
 #include "cb2_internal.cuh"
+#include "cb2_ptx.cuh"
 
 namespace cb2 {
 
-int tc_forward_layers(const cb2_model *, const cb2_batch *, const cb2_forward_io *, ForwardWs &, cudaStream_t) {
-  return fail(CB2_ERR_UNSUPPORTED, "tensor-core path not built yet");
+using namespace ptx;
+
+__device__ __forceinline__ float silu_fast(float x) {
+  // x * sigmoid(x) with ex2/rcp approximations (rel. error ~1e-6; inputs to an fp16 rounding)
+  return __fdividef(x, 1.0f + __expf(-x));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// =============================================================================================
+// k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 64 through a 4-stage ring.
+//   warps 0-3: load the A chunk (fp16 row-major global -> canonical smem), later the epilogue
+//   warp 4   : TMEM alloc, MMA issue (one lane)
+// =============================================================================================
+constexpr int TL_BM = 128, TL_NB = 256, TL_KC = 64, TL_STAGES = 4;
+constexpr int TL_A_BYTES = TL_BM * TL_KC * 2;   // 16 KB
+constexpr int TL_W_BYTES = TL_NB * TL_KC * 2;   // 32 KB
+constexpr int TL_STAGE_BYTES = TL_A_BYTES + TL_W_BYTES;
+constexpr int TL_SMEM = TL_STAGES * TL_STAGE_BYTES + 1024;
+
+struct TcLinearArgs {
+  const __half *A;
+  int64_t lda;
+  int64_t M;
+  int K;
+  const __half *Wt;   // operand image [K/8][Nw][8]
+  int Nw;
+  float *C;
+  int64_t ldc;
+  __half *C16;
+  int64_t ldc16;
+  const float *bias;
+  int silu;
+  const float *residual;
+  int64_t ldr;
+  const float *gbias;
+  const int32_t *gidx;
+  int gmod, gcols, gld;
+};
+
+__global__ void __launch_bounds__(160, 1) k_tc_linear(TcLinearArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + TL_STAGES * TL_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 64 + 8 * s; };
+  const uint32_t acc_bar = bar_base + 128;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TL_STAGES * TL_STAGE_BYTES + 192);
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int64_t m0 = (int64_t)blockIdx.x * TL_BM;
+  const int n0 = blockIdx.y * TL_NB;
+  const int nk = g.K / TL_KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < TL_STAGES; s++) {
+      mbar_init(full_bar(s), 129);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), TL_NB);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producer ----------------
+    const int r = tid;  // row of the tile
+    const int64_t grow = m0 + r;
+    const bool valid = grow < g.M;
+    const __half *arow = g.A + (valid ? grow : 0) * g.lda;
+    for (int kc = 0; kc < nk; kc++) {
+      const int s = kc % TL_STAGES;
+      mbar_wait(empty_bar(s), ((kc / TL_STAGES) & 1) ^ 1);
+      const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
+      const uint32_t w_s = a_s + TL_A_BYTES;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(full_bar(s), TL_W_BYTES);
+#pragma unroll
+        for (int k8 = 0; k8 < TL_KC / 8; k8++) {
+          const __half *src = g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8;
+          bulk_g2s(w_s + k8 * (TL_NB * 16), src, TL_NB * 16, full_bar(s));
+        }
+      }
+      uint4 v[8];
+#pragma unroll
+      for (int k8 = 0; k8 < 8; k8++)
+        v[k8] = valid ? *reinterpret_cast<const uint4 *>(arow + kc * TL_KC + k8 * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k8 = 0; k8 < 8; k8++)
+        *reinterpret_cast<uint4 *>(smem + s * TL_STAGE_BYTES + k8 * (TL_BM * 16) + r * 16) = v[k8];
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(s));
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(acc_bar, 0);
+    tc_fence_after_sync();
+    const float *gb = nullptr;
+    if (g.gbias != nullptr && valid) gb = g.gbias + (int64_t)g.gidx[grow % g.gmod] * g.gld;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TL_NB; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int c = n0 + c0 + j;
+        float x = __uint_as_float(acc[j]);
+        if (g.bias != nullptr) x += g.bias[c];
+        if (gb != nullptr && c < g.gcols) x += gb[c];
+        if (g.silu) x = silu_fast(x);
+        v[j] = x;
+      }
+      if (g.residual != nullptr) {
+        const float4 *rr = reinterpret_cast<const float4 *>(g.residual + grow * g.ldr + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float4 t = rr[j];
+          v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+        }
+      }
+      if (g.C != nullptr) {
+        float4 *cc = reinterpret_cast<float4 *>(g.C + grow * g.ldc + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) cc[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (g.C16 != nullptr) {
+        uint4 *cc = reinterpret_cast<uint4 *>(g.C16 + grow * g.ldc16 + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          cc[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+      }
+    }
+    tc_fence_before_sync();
+  } else {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32(TL_BM, TL_NB);
+      for (int kc = 0; kc < nk; kc++) {
+        const int s = kc % TL_STAGES;
+        mbar_wait(full_bar(s), (kc / TL_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
+        const uint32_t w_s = a_s + TL_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < TL_KC / 16; j++) {
+          const uint64_t ad = smem_desc_kmajor(a_s + 2 * j * (TL_BM * 16), TL_BM * 16, 128);
+          const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * (TL_NB * 16), TL_NB * 16, 128);
+          umma_f16(tmem, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TL_NB);
+}
+
+int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
+  if (a.M == 0) return CB2_OK;
+  if (a.K % TL_KC != 0 || a.Nw % TL_NB != 0 || (a.lda % 8) != 0)
+    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, lda%8 must be 0");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.M + TL_BM - 1) / TL_BM), (unsigned)(a.Nw / TL_NB));
+  k_tc_linear<<<grid, 160, TL_SMEM, st>>>(a);
+  CB2_LAUNCH_OK("k_tc_linear");
+  return CB2_OK;
+}
+
+// =============================================================================================
+// k_tc_edge: fused edge model of one CSPLayer for tiles of 128 edge rows (whole (i, all j)
+// segments of equal length n), persistent over (variant, tile) work items.
+//
+//   pre1 = P_i[i] + P_j[j] + W_fd emb(x_j - x_i)      GEMM1  [128 x 768] x [768 x 512]
+//   a1   = SiLU(pre1)  -> fp16, shared memory
+//   e    = SiLU(W2 a1 + b2)                           GEMM2  [128 x 512] x [512 x 512]
+//   agg_i = mean_j e_ij                               segmented mean, fp16 out
+//
+//   warps 0-7 : build the sinusoid A operand (rotation recurrence), both epilogues
+//   warp 8    : MMA issue (one lane), TMEM alloc     warp 9 : weight loader (bulk copies)
+// TMEM: one 128 x 512 fp32 accumulator (all 512 columns), used by GEMM1 then GEMM2.
+// =============================================================================================
+constexpr int TE_KC = 32;                       // K per pipeline stage
+constexpr int TE_WSTAGES = 3;
+constexpr int TE_W_BYTES = H * TE_KC * 2;       // 32 KB: [4][512][16 B]
+constexpr int TE_ASLOTS = 4;
+constexpr int TE_A_BYTES = 128 * TE_KC * 2;     // 8 KB: [4][128][16 B]
+constexpr int TE_AREGION = 128 * H * 2;         // 128 KB: a1 [64][128][16 B]
+constexpr int TE_T_OFF = TE_ASLOTS * TE_A_BYTES;            // transpose buffers after the emb ring
+constexpr int TE_T_PITCH = 33;
+constexpr int TE_T_BYTES = 128 * TE_T_PITCH * 4;            // one [128][33] fp32 buffer
+constexpr int TE_W_OFF = TE_AREGION;
+constexpr int TE_BAR_OFF = TE_W_OFF + TE_WSTAGES * TE_W_BYTES;
+constexpr int TE_SMEM = TE_BAR_OFF + 256 + 1024;            // barriers + tile row tables
+constexpr int TE_THREADS = 320;
+constexpr int TE_NCH1 = DIS / TE_KC;            // 24
+constexpr int TE_NCH2 = H / TE_KC;              // 16
+static_assert(TE_T_OFF + 4 * TE_T_BYTES <= TE_AREGION, "transpose buffers must fit the A region");
+
+struct TcEdgeArgs {
+  const float *P;          // [V*N,1024]
+  const float *x;          // [N,3]
+  const int32_t *row_i;    // [n_tiles*128]
+  const int32_t *row_j;
+  const int32_t *seg_n;    // [n_tiles]
+  const __half *w_fd_t;    // [96][512][8]
+  const __half *w2_t;      // [64][512][8]
+  const float *b2;
+  __half *agg16;           // [V*N, ld_agg], written at column offset agg_col
+  int64_t ld_agg;
+  int agg_col;
+  int N, V, n_tiles;
+};
+
+__global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + TE_BAR_OFF;
+  auto a_full = [&](int s) { return bars + 8 * s; };            // 4
+  auto a_empty = [&](int s) { return bars + 32 + 8 * s; };      // 4
+  auto w_full = [&](int s) { return bars + 64 + 8 * s; };       // 3
+  auto w_empty = [&](int s) { return bars + 96 + 8 * s; };      // 3
+  const uint32_t acc_full = bars + 128, a1_full = bars + 136, acc_empty = bars + 144;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 160);
+  int32_t *s_row_i = reinterpret_cast<int32_t *>(smem + TE_BAR_OFF + 256);
+  int32_t *s_row_j = s_row_i + 128;
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  if (tid == 0) {
+    for (int s = 0; s < TE_ASLOTS; s++) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < TE_WSTAGES; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(a1_full, 256);
+    mbar_init(acc_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = g.n_tiles * g.V;
+
+  if (warp == 9) {
+    // ------------------------------ weight loader ------------------------------
+    if (lane == 0) {
+      uint32_t wc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int c = 0; c < TE_NCH1 + TE_NCH2; c++, wc++) {
+          const int s = wc % TE_WSTAGES;
+          mbar_wait(w_empty(s), ((wc / TE_WSTAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(w_full(s), TE_W_BYTES);
+          const __half *src = (c < TE_NCH1) ? g.w_fd_t + (int64_t)c * (TE_W_BYTES / 2)
+                                            : g.w2_t + (int64_t)(c - TE_NCH1) * (TE_W_BYTES / 2);
+          bulk_g2s(sbase + TE_W_OFF + s * TE_W_BYTES, src, TE_W_BYTES, w_full(s));
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32(128, 256);
+      uint32_t wc = 0, ac = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        mbar_wait(acc_empty, (it & 1) ^ 1);   // previous item's E2 has drained the accumulator
+        tc_fence_after_sync();
+        // GEMM1: acc = emb W_fd^T
+        for (int kc = 0; kc < TE_NCH1; kc++, wc++, ac++) {
+          const int as = ac % TE_ASLOTS, ws = wc % TE_WSTAGES;
+          mbar_wait(a_full(as), (ac / TE_ASLOTS) & 1);
+          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_s = sbase + as * TE_A_BYTES, w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const uint64_t ad = smem_desc_kmajor(a_s + 2 * j * 2048, 2048, 128);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) {
+              const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * 8192 + nh * 4096, 8192, 128);
+              umma_f16(tmem + nh * 256, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(a_empty(as));
+          umma_commit(w_empty(ws));
+        }
+        umma_commit(acc_full);
+        // GEMM2: acc = a1 W2^T
+        mbar_wait(a1_full, it & 1);
+        tc_fence_after_sync();
+        for (int kc = 0; kc < TE_NCH2; kc++, wc++) {
+          const int ws = wc % TE_WSTAGES;
+          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
+          tc_fence_after_sync();
+          const uint32_t w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const uint64_t ad = smem_desc_kmajor(sbase + (kc * 4 + 2 * j) * 2048, 2048, 128);
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) {
+              const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * 8192 + nh * 4096, 8192, 128);
+              umma_f16(tmem + nh * 256, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(w_empty(ws));
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ------------------------------ workers (256 threads) ------------------------------
+    const int q = warp % 4, hh = warp / 4;    // TMEM lane quarter, column half / producer group
+    const int r = q * 32 + lane;              // row of the tile this thread owns
+    uint32_t ac = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int tile = item % g.n_tiles, v = item / g.n_tiles;
+      if (tid < 128) {
+        s_row_i[tid] = g.row_i[(int64_t)tile * 128 + tid];
+        s_row_j[tid] = g.row_j[(int64_t)tile * 128 + tid];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int ri = s_row_i[r], rj = s_row_j[r];
+      const bool valid = ri >= 0;
+      const int nseg_len = g.seg_n[tile];
+      // ---- phase 1: sinusoid embedding chunks (group hh builds chunks with kc % 2 == hh) ----
+      float dlt[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) dlt[d] = g.x[(int64_t)rj * 3 + d] - g.x[(int64_t)ri * 3 + d];
+      }
+      float s1 = 0.f, c1 = 1.f, s16 = 0.f, c16 = 1.f, sk = 0.f, ck = 1.f;
+      for (int kc = 0; kc < TE_NCH1; kc++, ac++) {
+        const int m = kc % 8;
+        if (m == 0) {
+          const float dd = dlt[kc / 8];
+          sincospif(2.0f * dd, &s1, &c1);
+          sincospif(32.0f * dd, &s16, &c16);
+          if (hh == 0) { sk = 0.f; ck = 1.f; } else { sk = s16; ck = c16; }
+        }
+        if ((m & 1) != hh) continue;
+        const int as = ac % TE_ASLOTS;
+        mbar_wait(a_empty(as), ((ac / TE_ASLOTS) & 1) ^ 1);
+        uint8_t *slot = smem + as * TE_A_BYTES + r * 16;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            w[e] = valid ? pack_half2(sk, ck) : 0u;
+            const float sn = fmaf(sk, c1, ck * s1);
+            const float cn = fmaf(ck, c1, -sk * s1);
+            sk = sn; ck = cn;
+          }
+          *reinterpret_cast<uint4 *>(slot + p * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        {  // jump over the other group's 16 frequencies
+          const float sn = fmaf(sk, c16, ck * s16);
+          const float cn = fmaf(ck, c16, -sk * s16);
+          sk = sn; ck = cn;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(a_full(as));
+      }
+      // ---- phase 2: E1  a1 = SiLU(acc + P_i + P_j) -> fp16 A operand of GEMM2 ----
+      mbar_wait(acc_full, 0);
+      tc_fence_after_sync();
+      {
+        const float *pi = g.P + ((int64_t)v * g.N + (valid ? ri : 0)) * H2 + hh * 256;
+        const float *pj = g.P + ((int64_t)v * g.N + (valid ? rj : 0)) * H2 + H + hh * 256;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          float4 a4[8], b4[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            a4[j] = *reinterpret_cast<const float4 *>(pi + c0 + 4 * j);
+            b4[j] = *reinterpret_cast<const float4 *>(pj + c0 + 4 * j);
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + hh * 256 + c0, acc);
+          tmem_ld_wait();
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            t[4 * j + 0] = silu_fast(__uint_as_float(acc[4 * j + 0]) + a4[j].x + b4[j].x);
+            t[4 * j + 1] = silu_fast(__uint_as_float(acc[4 * j + 1]) + a4[j].y + b4[j].y);
+            t[4 * j + 2] = silu_fast(__uint_as_float(acc[4 * j + 2]) + a4[j].z + b4[j].z);
+            t[4 * j + 3] = silu_fast(__uint_as_float(acc[4 * j + 3]) + a4[j].w + b4[j].w);
+          }
+          uint8_t *dst = smem + (size_t)((hh * 256 + c0) / 8) * 2048 + r * 16;
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            uint4 o = valid ? make_uint4(pack_half2(t[8 * p], t[8 * p + 1]), pack_half2(t[8 * p + 2], t[8 * p + 3]),
+                                         pack_half2(t[8 * p + 4], t[8 * p + 5]), pack_half2(t[8 * p + 6], t[8 * p + 7]))
+                            : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(dst + p * 2048) = o;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(a1_full);
+      // ---- phase 4: E2  e = SiLU(acc + b2); agg_i = mean_j e_ij ----
+      mbar_wait(acc_full, 1);
+      tc_fence_after_sync();
+      {
+        const int n = nseg_len;
+        const int S = 128 / n;
+        float *Tbuf = reinterpret_cast<float *>(smem + TE_T_OFF + hh * 2 * TE_T_BYTES);
+        const int tl = tid % 128;          // thread index within the half
+        const int cc = tl % 32, sg = tl / 32;
+        const float inv_n = 1.0f / (float)n;
+#pragma unroll 1
+        for (int blk = 0; blk < 8; blk++) {
+          const int c0 = hh * 256 + blk * 32;
+          uint32_t acc[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, acc);
+          tmem_ld_wait();
+          float *T = Tbuf + (blk & 1) * (128 * TE_T_PITCH);
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            T[r * TE_T_PITCH + j] = silu_fast(__uint_as_float(acc[j]) + __ldg(g.b2 + c0 + j));
+          if (blk == 7) {
+            tc_fence_before_sync();
+            mbar_arrive(acc_empty);      // accumulator fully read: the next item's GEMM1 may start
+          }
+          if (hh == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else asm volatile("bar.sync 3, 128;" ::: "memory");
+          for (int s = sg; s < S; s += 4) {
+            const int node = s_row_i[s * n];
+            if (node < 0) continue;
+            float sum = 0.f;
+            const float *col = T + (s * n) * TE_T_PITCH + cc;
+            for (int jj = 0; jj < n; jj++) sum += col[jj * TE_T_PITCH];
+            g.agg16[((int64_t)v * g.N + node) * g.ld_agg + g.agg_col + c0 + cc] = __float2half_rn(sum * inv_n);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // row tables / T buffers free for the next item
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {
+  const int n_items = a.n_tiles * a.V;
+  if (n_items == 0) return CB2_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
+    attr_set = true;
+  }
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  k_tc_edge<<<grid, TE_THREADS, TE_SMEM, st>>>(a);
+  CB2_LAUNCH_OK("k_tc_edge");
+  return CB2_OK;
+}
+
+// launchers from cb2_kernels_f32.cu reused by the tensor-core path
+int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
+                      const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
+                      int64_t ld_hn16, int N, int B, int V, cudaStream_t st);
+int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
+int launch_to_half(const float *x, __half *y, int64_t n, cudaStream_t st);
+
+static int g_num_sms = 0;
+
+static int num_sms(int *out) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CB2_CUDA_OK(cudaGetDevice(&dev));
+    CB2_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  *out = g_num_sms;
+  return CB2_OK;
+}
+
+int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
+                     int64_t ldc, int64_t M, int K, int silu, cudaStream_t st) {
+  TcLinearArgs a{};
+  a.A = (const __half *)A16; a.lda = lda; a.M = M; a.K = K; a.Wt = (const __half *)Wt; a.Nw = Nw;
+  a.C = C; a.ldc = ldc; a.bias = bias; a.silu = silu;
+  return launch_tc_linear(a, st);
+}
+
+int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
+                  int64_t ld_agg, int agg_col, cudaStream_t st) {
+  int sms = 0;
+  CB2_TRY(num_sms(&sms));
+  TcEdgeArgs e{};
+  e.P = P; e.x = x; e.row_i = b->tile_row_i; e.row_j = b->tile_row_j; e.seg_n = b->tile_seg_n;
+  e.w_fd_t = (const __half *)L.w_fd_t; e.w2_t = (const __half *)L.w2_t; e.b2 = L.b2;
+  e.agg16 = agg16; e.ld_agg = ld_agg; e.agg_col = agg_col; e.N = b->n_nodes; e.V = b->n_variants;
+  e.n_tiles = b->n_tiles;
+  return launch_tc_edge(e, sms, st);
+}
+
+int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
+                      cudaStream_t st) {
+  const int N = b->n_nodes, B = b->n_graphs, V = b->n_variants;
+  const int64_t VN = (int64_t)V * N;
+  if (!m->film_wp_t) return fail(CB2_ERR_BAD_ARG, "tensor-core path needs the fp16 operand images (pack with tensor_core=True)");
+  CB2_TRY(launch_to_half(w.h, w.h16, VN * H, st));
+  for (int li = 0; li < m->n_layers; li++) {
+    const cb2_layer_weights &L = m->layers[li];
+    if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
+      return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
+    if (io->film_cond != nullptr) {
+      TcLinearArgs a{};
+      a.A = w.h16; a.lda = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
+      a.C = w.y; a.ldc = H; a.bias = m->film_bp;
+      CB2_TRY(launch_tc_linear(a, st));
+    }
+    CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
+                              nullptr, 0, w.cat16, H2, N, B, V, st));
+    CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
+    {
+      TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T  (+ lattice term + b1 on the P_i half)
+      a.A = w.cat16; a.lda = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
+      a.C = w.P; a.ldc = H2;
+      a.gbias = w.cg; a.gidx = b->node2graph; a.gmod = N; a.gcols = H; a.gld = H;
+      CB2_TRY(launch_tc_linear(a, st));
+    }
+    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, w.P, w.cat16, H2, H, st));
+    {
+      TcLinearArgs a{};   // z = SiLU([hn|agg] Wn1^T + bn1)
+      a.A = w.cat16; a.lda = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;
+      a.C16 = w.z16; a.ldc16 = H; a.bias = L.bn1; a.silu = 1;
+      CB2_TRY(launch_tc_linear(a, st));
+      TcLinearArgs a2{};  // h = h + SiLU(z Wn2^T + bn2)
+      a2.A = w.z16; a2.lda = H; a2.M = VN; a2.K = H; a2.Wt = (const __half *)L.wn2_t; a2.Nw = H;
+      a2.C = w.h; a2.ldc = H; a2.C16 = w.h16; a2.ldc16 = H; a2.bias = L.bn2; a2.silu = 1;
+      a2.residual = w.h; a2.ldr = H;
+      CB2_TRY(launch_tc_linear(a2, st));
+    }
+  }
+  return CB2_OK;
 }
 
 }  // namespace cb2

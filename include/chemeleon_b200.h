@@ -182,6 +182,21 @@ int cb2_film_cond(const cb2_model *m, const cb2_batch *b, const float *text_part
 int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bias, float *C,
                    int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t silu, void *stream);
 
+/* C = act(A16 W16^T + bias) on the tensor cores (tcgen05, fp32 accumulate).  A16: fp16
+ * row-major [M,lda]; Wt: fp16 operand image [K/8][Nw][8] of a torch Linear weight [Nw,K]
+ * (weights.tile_k_major); K % 64 == 0, Nw % 256 == 0.  The building block of the
+ * node-level GEMMs (FilmLayer.proj, hoisted W1 blocks, node_mlp; cspnet.py:86,113,120). */
+int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
+                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream);
+
+/* Edge model + scatter_mean of ONE CSPLayer (CSPLayer.edge_model + the aggregation in
+ * node_model, cspnet.py:129-160) from the hoisted node terms P [V*N,1024] = (P_i | P_j):
+ *   agg_i = mean_j SiLU(W2 SiLU(P_i[i] + P_j[j] + W_fd emb(x_j - x_i)) + b2).
+ * precision FP32: agg is float [V*N, ld_agg]; TC_F16: agg is fp16 [V*N, ld_agg]. */
+int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
+                   const float *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
 /* One CSPNet.forward (cspnet.py:345-405) for all V variants of the batch. */
 int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io,
                         void *workspace, size_t workspace_bytes, void *stream);
