@@ -119,6 +119,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// two floats -> packed fp16x2 (a in the low half), saturating to +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 __device__ __forceinline__ float wrap01(float v) {
   // torch's float remainder(v, 1.0): fmod, then shift negatives up by 1.
   float r = fmodf(v, 1.0f);

@@ -218,11 +218,9 @@ __device__ __forceinline__ void store_row(float *__restrict__ p, const float (&v
 __device__ __forceinline__ void store_row_half(__half *__restrict__ p, const float (&v)[16], int lane) {
 #pragma unroll
   for (int q4 = 0; q4 < 4; q4++) {
-    __half2 lo = __floats2half2_rn(v[q4 * 4 + 0], v[q4 * 4 + 1]);
-    __half2 hi = __floats2half2_rn(v[q4 * 4 + 2], v[q4 * 4 + 3]);
     uint2 u;
-    u.x = *reinterpret_cast<uint32_t *>(&lo);
-    u.y = *reinterpret_cast<uint32_t *>(&hi);
+    u.x = pack_half2_sat(v[q4 * 4 + 0], v[q4 * 4 + 1]);
+    u.y = pack_half2_sat(v[q4 * 4 + 2], v[q4 * 4 + 3]);
     *reinterpret_cast<uint2 *>(p + (lane + 32 * q4) * 4) = u;
   }
 }
@@ -436,10 +434,9 @@ __global__ void k_to_half(const float *__restrict__ x, __half *__restrict__ y, i
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = reinterpret_cast<const float4 *>(x)[i];
-  __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
   uint2 u;
-  u.x = *reinterpret_cast<uint32_t *>(&lo);
-  u.y = *reinterpret_cast<uint32_t *>(&hi);
+  u.x = pack_half2_sat(v.x, v.y);
+  u.y = pack_half2_sat(v.z, v.w);
   reinterpret_cast<uint2 *>(y)[i] = u;
 }
 

@@ -21,10 +21,7 @@ __device__ __forceinline__ float silu_fast(float x) {
   return __fdividef(x, 1.0f + __expf(-x));
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t *>(&h);
-}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) { return pack_half2_sat(a, b); }
 
 // =============================================================================================
 // k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 64 through a 4-stage ring.
@@ -467,7 +464,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
             float sum = 0.f;
             const float *col = T + (s * n) * TE_T_PITCH + cc;
             for (int jj = 0; jj < n; jj++) sum += col[jj * TE_T_PITCH];
-            g.agg16[((int64_t)v * g.N + node) * g.ld_agg + g.agg_col + c0 + cc] = __float2half_rn(sum * inv_n);
+            g.agg16[((int64_t)v * g.N + node) * g.ld_agg + g.agg_col + c0 + cc] =
+                __float2half_rn(fminf(fmaxf(sum * inv_n, -65504.f), 65504.f));
           }
         }
       }

@@ -31,7 +31,7 @@ Tensor = torch.Tensor
 
 
 def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, head_scale: float = 1.0,
-                           perturb_ln: bool = True) -> Dict[str, Tensor]:
+                           perturb_ln: bool = True, lattice_identity: bool = False) -> Dict[str, Tensor]:
     """Random weights of the reference architecture, keyed like its checkpoint.
 
     Checkpoints are not available offline, so benchmarks and parity tests use
@@ -74,6 +74,15 @@ def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, 
     lin("decoder.coord_out", 3, H, bias=False, scale=head_scale)
     lin("decoder.lattice_out", 9, H, bias=False, scale=head_scale)
     lin("decoder.type_out", A, H, scale=head_scale)
+    if lattice_identity:
+        # An untrained lattice head predicts ~0 noise, so the ancestral DDPM step
+        # (chemeleon.py:420) multiplies the lattice by prod 1/sqrt(alpha_t) ~ 1e3 over the
+        # run.  Make the head behave like a trained denoiser for data at the origin:
+        # feature 0 of the final LayerNorm is the constant 4 and lattice_out maps it to
+        # vec(I)/4, so lattice_out ~= I @ L and the step is a contraction (|l| stays O(1)).
+        sd["decoder.final_layer_norm.weight"][0] = 0.0
+        sd["decoder.final_layer_norm.bias"][0] = 4.0
+        sd["decoder.lattice_out.weight"][:, 0] = torch.eye(3).reshape(9) / 4.0
     sx = schedules.sigma_buffer(cfg.timesteps, cfg.sigma_begin, cfg.sigma_end)
     sd["sigma_scheduler.sigmas"] = sx
     sd["sigma_scheduler.sigmas_norm"] = schedules.sigma_norm_monte_carlo(sx[1:], seed=seed)

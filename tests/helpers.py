@@ -8,7 +8,7 @@ from chemeleon_b200.config import SamplerConfig
 from chemeleon_b200.weights import random_init_state_dict
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["c1_tamed_1000", "c1_full_6", "ragged_full_4"]
+GOLDEN_CASES = ["c1_tamed_1000", "c1_bounded_1000", "c1_full_6", "ragged_full_4"]
 
 
 def load_golden(name):
@@ -25,7 +25,8 @@ def weight_checksum(sd):
 
 def golden_weights(g):
     """Regenerate the fixture's weights from its seed and verify the checksum."""
-    sd = random_init_state_dict(SamplerConfig(), seed=int(g["weight_seed"]), head_scale=float(g["head_scale"]))
+    sd = random_init_state_dict(SamplerConfig(), seed=int(g["weight_seed"]), head_scale=float(g["head_scale"]),
+                                 lattice_identity=bool(int(g["lattice_identity"])) if "lattice_identity" in g else False)
     cs = weight_checksum(sd)
     assert np.allclose(cs, g["weight_checksum"], rtol=1e-12, atol=0), \
         f"regenerated weights differ from the fixture's ({cs} vs {g['weight_checksum']})"
