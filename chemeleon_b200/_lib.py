@@ -72,7 +72,7 @@ class StepArgs(C.Structure):
         ("cond_scale", C.c_float), ("timesteps", C.c_int32), ("precision", C.c_int32),
         ("noise_mode", C.c_int32), ("t_start", C.c_int32),
         ("rand_a", vp), ("rand_l", vp), ("rand_x", vp), ("rand_x2", vp),
-        ("seed", C.c_uint64), ("graph_gid", vp),
+        ("seed", C.c_uint64), ("seed_dev", vp), ("graph_gid", vp),
     ]
 
 

@@ -9,19 +9,11 @@
 //
 // Shared-memory operand layout everywhere: K-major, no swizzle, [K/8][rows][8 halves]
 // (core matrix = 8 rows x 16 B; SBO = 128 B, LBO = rows*16 B).
-#include "cb2_internal.cuh"
-#include "cb2_ptx.cuh"
+#include "cb2_tc.cuh"
 
 namespace cb2 {
 
 using namespace ptx;
-
-__device__ __forceinline__ float silu_fast(float x) {
-  // x * sigmoid(x) with ex2/rcp approximations (rel. error ~1e-6; inputs to an fp16 rounding)
-  return __fdividef(x, 1.0f + __expf(-x));
-}
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) { return pack_half2_sat(a, b); }
 
 // =============================================================================================
 // k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 64 through a 4-stage ring.
@@ -195,299 +187,6 @@ int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
   dim3 grid((unsigned)((a.M + TL_BM - 1) / TL_BM), (unsigned)(a.Nw / TL_NB));
   k_tc_linear<<<grid, 160, TL_SMEM, st>>>(a);
   CB2_LAUNCH_OK("k_tc_linear");
-  return CB2_OK;
-}
-
-// =============================================================================================
-// k_tc_edge: fused edge model of one CSPLayer for tiles of 128 edge rows (whole (i, all j)
-// segments of equal length n), persistent over (variant, tile) work items.
-//
-//   pre1 = P_i[i] + P_j[j] + W_fd emb(x_j - x_i)      GEMM1  [128 x 768] x [768 x 512]
-//   a1   = SiLU(pre1)  -> fp16, shared memory
-//   e    = SiLU(W2 a1 + b2)                           GEMM2  [128 x 512] x [512 x 512]
-//   agg_i = mean_j e_ij                               segmented mean, fp16 out
-//
-//   warps 0-7 : build the sinusoid A operand (rotation recurrence), both epilogues
-//   warp 8    : MMA issue (one lane), TMEM alloc     warp 9 : weight loader (bulk copies)
-// TMEM: one 128 x 512 fp32 accumulator (all 512 columns), used by GEMM1 then GEMM2.
-// =============================================================================================
-constexpr int TE_KC = 32;                       // K per pipeline stage
-constexpr int TE_WSTAGES = 3;
-constexpr int TE_W_BYTES = H * TE_KC * 2;       // 32 KB: [4][512][16 B]
-constexpr int TE_ASLOTS = 4;
-constexpr int TE_A_BYTES = 128 * TE_KC * 2;     // 8 KB: [4][128][16 B]
-constexpr int TE_AREGION = 128 * H * 2;         // 128 KB: a1 [64][128][16 B]
-constexpr int TE_T_OFF = TE_ASLOTS * TE_A_BYTES;            // transpose buffers after the emb ring
-constexpr int TE_T_PITCH = 33;
-constexpr int TE_T_BYTES = 128 * TE_T_PITCH * 4;            // one [128][33] fp32 buffer
-constexpr int TE_W_OFF = TE_AREGION;
-constexpr int TE_BAR_OFF = TE_W_OFF + TE_WSTAGES * TE_W_BYTES;
-constexpr int TE_SMEM = TE_BAR_OFF + 256 + 1024;            // barriers + tile row tables
-constexpr int TE_THREADS = 320;
-constexpr int TE_NCH1 = DIS / TE_KC;            // 24
-constexpr int TE_NCH2 = H / TE_KC;              // 16
-static_assert(TE_T_OFF + 4 * TE_T_BYTES <= TE_AREGION, "transpose buffers must fit the A region");
-
-struct TcEdgeArgs {
-  const float *P;          // [V*N,1024]
-  const float *x;          // [N,3]
-  const int32_t *row_i;    // [n_tiles*128]
-  const int32_t *row_j;
-  const int32_t *seg_n;    // [n_tiles]
-  const __half *w_fd_t;    // [96][512][8]
-  const __half *w2_t;      // [64][512][8]
-  const float *b2;
-  __half *agg16;           // [V*N, ld_agg], written at column offset agg_col
-  int64_t ld_agg;
-  int agg_col;
-  int N, V, n_tiles;
-};
-
-__global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + TE_BAR_OFF;
-  auto a_full = [&](int s) { return bars + 8 * s; };            // 4
-  auto a_empty = [&](int s) { return bars + 32 + 8 * s; };      // 4
-  auto w_full = [&](int s) { return bars + 64 + 8 * s; };       // 3
-  auto w_empty = [&](int s) { return bars + 96 + 8 * s; };      // 3
-  const uint32_t acc_full = bars + 128, a1_full = bars + 136, acc_empty = bars + 144;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 160);
-  int32_t *s_row_i = reinterpret_cast<int32_t *>(smem + TE_BAR_OFF + 256);
-  int32_t *s_row_j = s_row_i + 128;
-
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  if (tid == 0) {
-    for (int s = 0; s < TE_ASLOTS; s++) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < TE_WSTAGES; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(a1_full, 256);
-    mbar_init(acc_empty, 256);
-    fence_barrier_init();
-  }
-  if (warp == 8) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const int n_items = g.n_tiles * g.V;
-
-  if (warp == 9) {
-    // ------------------------------ weight loader ------------------------------
-    if (lane == 0) {
-      uint32_t wc = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int c = 0; c < TE_NCH1 + TE_NCH2; c++, wc++) {
-          const int s = wc % TE_WSTAGES;
-          mbar_wait(w_empty(s), ((wc / TE_WSTAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(w_full(s), TE_W_BYTES);
-          const __half *src = (c < TE_NCH1) ? g.w_fd_t + (int64_t)c * (TE_W_BYTES / 2)
-                                            : g.w2_t + (int64_t)(c - TE_NCH1) * (TE_W_BYTES / 2);
-          bulk_g2s(sbase + TE_W_OFF + s * TE_W_BYTES, src, TE_W_BYTES, w_full(s));
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_f16_f32(128, 256);
-      uint32_t wc = 0, ac = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        mbar_wait(acc_empty, (it & 1) ^ 1);   // previous item's E2 has drained the accumulator
-        tc_fence_after_sync();
-        // GEMM1: acc = emb W_fd^T
-        for (int kc = 0; kc < TE_NCH1; kc++, wc++, ac++) {
-          const int as = ac % TE_ASLOTS, ws = wc % TE_WSTAGES;
-          mbar_wait(a_full(as), (ac / TE_ASLOTS) & 1);
-          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
-          tc_fence_after_sync();
-          const uint32_t a_s = sbase + as * TE_A_BYTES, w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            const uint64_t ad = smem_desc_kmajor(a_s + 2 * j * 2048, 2048, 128);
-#pragma unroll
-            for (int nh = 0; nh < 2; nh++) {
-              const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * 8192 + nh * 4096, 8192, 128);
-              umma_f16(tmem + nh * 256, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
-            }
-          }
-          umma_commit(a_empty(as));
-          umma_commit(w_empty(ws));
-        }
-        umma_commit(acc_full);
-        // GEMM2: acc = a1 W2^T
-        mbar_wait(a1_full, it & 1);
-        tc_fence_after_sync();
-        for (int kc = 0; kc < TE_NCH2; kc++, wc++) {
-          const int ws = wc % TE_WSTAGES;
-          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
-          tc_fence_after_sync();
-          const uint32_t w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            const uint64_t ad = smem_desc_kmajor(sbase + (kc * 4 + 2 * j) * 2048, 2048, 128);
-#pragma unroll
-            for (int nh = 0; nh < 2; nh++) {
-              const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * 8192 + nh * 4096, 8192, 128);
-              umma_f16(tmem + nh * 256, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
-            }
-          }
-          umma_commit(w_empty(ws));
-        }
-        umma_commit(acc_full);
-      }
-    }
-  } else {
-    // ------------------------------ workers (256 threads) ------------------------------
-    const int q = warp % 4, hh = warp / 4;    // TMEM lane quarter, column half / producer group
-    const int r = q * 32 + lane;              // row of the tile this thread owns
-    uint32_t ac = 0, it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-      const int tile = item % g.n_tiles, v = item / g.n_tiles;
-      if (tid < 128) {
-        s_row_i[tid] = g.row_i[(int64_t)tile * 128 + tid];
-        s_row_j[tid] = g.row_j[(int64_t)tile * 128 + tid];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int ri = s_row_i[r], rj = s_row_j[r];
-      const bool valid = ri >= 0;
-      const int nseg_len = g.seg_n[tile];
-      // ---- phase 1: sinusoid embedding chunks (group hh builds chunks with kc % 2 == hh) ----
-      float dlt[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) dlt[d] = g.x[(int64_t)rj * 3 + d] - g.x[(int64_t)ri * 3 + d];
-      }
-      float s1 = 0.f, c1 = 1.f, s16 = 0.f, c16 = 1.f, sk = 0.f, ck = 1.f;
-      for (int kc = 0; kc < TE_NCH1; kc++, ac++) {
-        const int m = kc % 8;
-        if (m == 0) {
-          const float dd = dlt[kc / 8];
-          sincospif(2.0f * dd, &s1, &c1);
-          sincospif(32.0f * dd, &s16, &c16);
-          if (hh == 0) { sk = 0.f; ck = 1.f; } else { sk = s16; ck = c16; }
-        }
-        if ((m & 1) != hh) continue;
-        const int as = ac % TE_ASLOTS;
-        mbar_wait(a_empty(as), ((ac / TE_ASLOTS) & 1) ^ 1);
-        uint8_t *slot = smem + as * TE_A_BYTES + r * 16;
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            w[e] = valid ? pack_half2(sk, ck) : 0u;
-            const float sn = fmaf(sk, c1, ck * s1);
-            const float cn = fmaf(ck, c1, -sk * s1);
-            sk = sn; ck = cn;
-          }
-          *reinterpret_cast<uint4 *>(slot + p * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        {  // jump over the other group's 16 frequencies
-          const float sn = fmaf(sk, c16, ck * s16);
-          const float cn = fmaf(ck, c16, -sk * s16);
-          sk = sn; ck = cn;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(a_full(as));
-      }
-      // ---- phase 2: E1  a1 = SiLU(acc + P_i + P_j) -> fp16 A operand of GEMM2 ----
-      mbar_wait(acc_full, 0);
-      tc_fence_after_sync();
-      {
-        const float *pi = g.P + ((int64_t)v * g.N + (valid ? ri : 0)) * H2 + hh * 256;
-        const float *pj = g.P + ((int64_t)v * g.N + (valid ? rj : 0)) * H2 + H + hh * 256;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          float4 a4[8], b4[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            a4[j] = *reinterpret_cast<const float4 *>(pi + c0 + 4 * j);
-            b4[j] = *reinterpret_cast<const float4 *>(pj + c0 + 4 * j);
-          }
-          uint32_t acc[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + hh * 256 + c0, acc);
-          tmem_ld_wait();
-          float t[32];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            t[4 * j + 0] = silu_fast(__uint_as_float(acc[4 * j + 0]) + a4[j].x + b4[j].x);
-            t[4 * j + 1] = silu_fast(__uint_as_float(acc[4 * j + 1]) + a4[j].y + b4[j].y);
-            t[4 * j + 2] = silu_fast(__uint_as_float(acc[4 * j + 2]) + a4[j].z + b4[j].z);
-            t[4 * j + 3] = silu_fast(__uint_as_float(acc[4 * j + 3]) + a4[j].w + b4[j].w);
-          }
-          uint8_t *dst = smem + (size_t)((hh * 256 + c0) / 8) * 2048 + r * 16;
-#pragma unroll
-          for (int p = 0; p < 4; p++) {
-            uint4 o = valid ? make_uint4(pack_half2(t[8 * p], t[8 * p + 1]), pack_half2(t[8 * p + 2], t[8 * p + 3]),
-                                         pack_half2(t[8 * p + 4], t[8 * p + 5]), pack_half2(t[8 * p + 6], t[8 * p + 7]))
-                            : make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4 *>(dst + p * 2048) = o;
-          }
-        }
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(a1_full);
-      // ---- phase 4: E2  e = SiLU(acc + b2); agg_i = mean_j e_ij ----
-      mbar_wait(acc_full, 1);
-      tc_fence_after_sync();
-      {
-        const int n = nseg_len;
-        const int S = 128 / n;
-        float *Tbuf = reinterpret_cast<float *>(smem + TE_T_OFF + hh * 2 * TE_T_BYTES);
-        const int tl = tid % 128;          // thread index within the half
-        const int cc = tl % 32, sg = tl / 32;
-        const float inv_n = 1.0f / (float)n;
-#pragma unroll 1
-        for (int blk = 0; blk < 8; blk++) {
-          const int c0 = hh * 256 + blk * 32;
-          uint32_t acc[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, acc);
-          tmem_ld_wait();
-          float *T = Tbuf + (blk & 1) * (128 * TE_T_PITCH);
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            T[r * TE_T_PITCH + j] = silu_fast(__uint_as_float(acc[j]) + __ldg(g.b2 + c0 + j));
-          if (blk == 7) {
-            tc_fence_before_sync();
-            mbar_arrive(acc_empty);      // accumulator fully read: the next item's GEMM1 may start
-          }
-          if (hh == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else asm volatile("bar.sync 3, 128;" ::: "memory");
-          for (int s = sg; s < S; s += 4) {
-            const int node = s_row_i[s * n];
-            if (node < 0) continue;
-            float sum = 0.f;
-            const float *col = T + (s * n) * TE_T_PITCH + cc;
-            for (int jj = 0; jj < n; jj++) sum += col[jj * TE_T_PITCH];
-            g.agg16[((int64_t)v * g.N + node) * g.ld_agg + g.agg_col + c0 + cc] =
-                __float2half_rn(fminf(fmaxf(sum * inv_n, -65504.f), 65504.f));
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // row tables / T buffers free for the next item
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
-}
-
-int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {
-  const int n_items = a.n_tiles * a.V;
-  if (n_items == 0) return CB2_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
-    attr_set = true;
-  }
-  const int grid = n_items < n_sm ? n_items : n_sm;
-  k_tc_edge<<<grid, TE_THREADS, TE_SMEM, st>>>(a);
-  CB2_LAUNCH_OK("k_tc_edge");
   return CB2_OK;
 }
 

@@ -1,0 +1,348 @@
+// k_tc_edge: fused edge model + scatter_mean of one CSPLayer on the tensor cores
+// (CSPLayer.edge_model and the aggregation of node_model, cspnet.py:129-160).
+//
+// Work item = (variant, tile); a tile is 128 edge rows = whole (i, all j) segments of equal
+// length n, generated on the fly from the per-tile (i, j) row tables -- no edge_index,
+// nothing of size O(E) ever touches HBM.  TMEM lanes = output channels, TMEM columns = edges
+// ("transposed" orientation), four 128-channel x 128-edge fp32 units U0..U3 = all 512 columns.
+//
+//   init   U_m    = P_i[i] + P_j[j]          tcgen05.st, thread = channel (coalesced gathers);
+//                                            done for tile t+1 while GEMM2 of tile t runs
+//   GEMM1  U_m   += W_fd[m] emb^T            A = weights (K-major image, bulk-copied, UBLKCP)
+//                                            B = sinusoid embedding built in smem by a rotation
+//                                                recurrence (thread = edge row), K-major
+//   E1     a1     = SiLU(U) -> fp16          MN-major B operand of GEMM2 in smem
+//   GEMM2  U_m'   = W2[m'] a1^T              one unit after the other, so that
+//   E2     agg_i  = mean_j SiLU(U + b2)      E2 of unit m' overlaps GEMM2 of unit m'+1;
+//                                            the segmented mean is an in-thread running sum
+//
+//   warps 0-15: worker warp w owns TMEM lane quarter w%4 of unit w/4 (init, E1, E2) and, as
+//               member of embedding group w/4, the edge row (w%4)*32+lane of every 4th K chunk
+//   warp 16   : MMA issue (one lane), TMEM alloc        warp 17: weight loader (bulk copies)
+#include "cb2_tc.cuh"
+
+namespace cb2 {
+
+using namespace ptx;
+
+constexpr int TE_KC = 32;                       // K per GEMM1 pipeline stage
+constexpr int TE_WSTAGES = 3;
+constexpr int TE_W_BYTES = 32768;               // GEMM1: [4 k8][512 ch][16 B]; GEMM2: [16 k8][128 ch][16 B]
+constexpr int TE_ASLOTS = 4;                    // one slot per embedding group
+constexpr int TE_A_BYTES = 128 * TE_KC * 2;     // 8 KB: [4 k8][128 edges][16 B]
+constexpr int TE_AREGION = 128 * H * 2;         // 128 KB: a1, MN-major [64 k8][16 e8][8 k][8 e]
+constexpr int TE_W_OFF = TE_AREGION;
+constexpr int TE_BAR_OFF = TE_W_OFF + TE_WSTAGES * TE_W_BYTES;
+constexpr int TE_TAB_OFF = TE_BAR_OFF + 256;    // 2 buffers x (off_i[128], off_j[128]) uint32
+constexpr int TE_SMEM = TE_TAB_OFF + 2 * 1024;
+constexpr int TE_WORKERS = 512;
+constexpr int TE_THREADS = TE_WORKERS + 64;
+constexpr int TE_NCH1 = DIS / TE_KC;            // 24 stages of K=32
+constexpr int TE_NCH2 = 4;                      // per output unit: 4 stages of K=128
+constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
+static_assert(TE_SMEM <= 232448, "shared memory budget");
+
+__host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
+
+#define TE_WORKER_BARRIER() asm volatile("bar.sync 1, 512;" ::: "memory")
+
+__global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + TE_BAR_OFF;
+  auto a_full = [&](int s) { return bars + 8 * s; };
+  auto a_empty = [&](int s) { return bars + 32 + 8 * s; };
+  auto w_full = [&](int s) { return bars + 64 + 8 * s; };
+  auto w_empty = [&](int s) { return bars + 96 + 8 * s; };
+  const uint32_t acc1_full = bars + 128, a1_ready = bars + 136;
+  auto acc2_full = [&](int u) { return bars + 144 + 8 * u; };
+  auto acc_init = [&](int u) { return bars + 176 + 8 * u; };
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 208);
+  uint32_t *tab = reinterpret_cast<uint32_t *>(smem + TE_TAB_OFF);   // [buf][0: off_i, 1: off_j][128]
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  if (tid == 0) {
+    for (int s = 0; s < TE_ASLOTS; s++) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < TE_WSTAGES; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    mbar_init(acc1_full, 1);
+    mbar_init(a1_ready, TE_WORKERS);
+    for (int u = 0; u < 4; u++) { mbar_init(acc2_full(u), 1); mbar_init(acc_init(u), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 16) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = g.n_tiles * g.V;
+
+  if (warp == 17) {
+    // ------------------------------ weight loader ------------------------------
+    if (lane == 0) {
+      uint32_t wc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int c = 0; c < TE_NCH1 + 4 * TE_NCH2; c++, wc++) {
+          const int s = wc % TE_WSTAGES;
+          mbar_wait(w_empty(s), ((wc / TE_WSTAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(w_full(s), TE_W_BYTES);
+          const __half *src = (c < TE_NCH1) ? g.w_fd_t + (int64_t)c * (TE_W_BYTES / 2)
+                                            : g.w2_t + (int64_t)(c - TE_NCH1) * (TE_W_BYTES / 2);
+          bulk_g2s(sbase + TE_W_OFF + s * TE_W_BYTES, src, TE_W_BYTES, w_full(s));
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = idesc_f16_f32(128, 128);
+      constexpr uint32_t idesc_kmn = idesc_b_mn(idesc_f16_f32(128, 128));
+      uint32_t wc = 0, ac = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        for (int u = 0; u < 4; u++) mbar_wait(acc_init(u), it & 1);   // units hold P_i + P_j
+        tc_fence_after_sync();
+        // GEMM1: U_m += W_fd[m] emb^T, all four units per K chunk
+        for (int kc = 0; kc < TE_NCH1; kc++, wc++, ac++) {
+          const int as = ac % TE_ASLOTS, ws = wc % TE_WSTAGES;
+          mbar_wait(a_full(as), (ac / TE_ASLOTS) & 1);
+          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
+          tc_fence_after_sync();
+          const uint32_t e_s = sbase + as * TE_A_BYTES, w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const uint64_t bd = smem_desc_kmajor(e_s + 2 * j * 2048, 2048, 128);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+              const uint64_t ad = smem_desc_kmajor(w_s + 2 * j * 8192 + m * 2048, 8192, 128);
+              umma_f16(tmem + m * 128, ad, bd, idesc_kk, 1u);
+            }
+          }
+          umma_commit(a_empty(as));
+          umma_commit(w_empty(ws));
+        }
+        umma_commit(acc1_full);
+        // GEMM2: U_m' = W2[m'] a1^T, unit after unit
+        mbar_wait(a1_ready, it & 1);
+        tc_fence_after_sync();
+        for (int u = 0; u < 4; u++) {
+          for (int kc = 0; kc < TE_NCH2; kc++, wc++) {
+            const int ws = wc % TE_WSTAGES;
+            mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
+            tc_fence_after_sync();
+            const uint32_t w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint64_t ad = smem_desc_kmajor(w_s + 2 * j * 2048, 2048, 128);
+              const uint64_t bd = smem_desc_kmajor(sbase + (kc * 16 + 2 * j) * 2048, 2048, 128);
+              umma_f16(tmem + u * 128, ad, bd, idesc_kmn, (kc > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(w_empty(ws));
+          }
+          umma_commit(acc2_full(u));
+        }
+      }
+    }
+  } else {
+    // ------------------------------ workers (512 threads) ------------------------------
+    const int q = warp % 4, u4 = warp / 4;       // TMEM lane quarter; unit / embedding group
+    const int r = q * 32 + lane;                 // edge row owned while producing the embedding
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + u4 * 128;
+    const int c = u4 * 128 + q * 32 + lane;      // output channel owned in the epilogues
+    const float *Pc = g.P + c;
+    const float bias = __ldg(g.b2 + c);
+    __half *out = g.agg16 + g.agg_col + c;
+    uint8_t *a1_dst = smem + (size_t)(c / 8) * 2048 + (c % 8) * 16;
+
+    // row tables of one tile -> buffer `buf` (group 0 writes them); every thread keeps the
+    // fractional-coordinate difference of its row in registers
+    auto load_tables = [&](int item, int buf, float (&dl)[3]) {
+      const int tile = item % g.n_tiles, v = item / g.n_tiles;
+      const int ri = g.row_i[(int64_t)tile * 128 + r], rj = g.row_j[(int64_t)tile * 128 + r];
+      dl[0] = dl[1] = dl[2] = 0.f;
+      if (ri >= 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) dl[d] = g.x[(int64_t)rj * 3 + d] - g.x[(int64_t)ri * 3 + d];
+      }
+      if (u4 == 0) {
+        const uint32_t vbase = (uint32_t)v * (uint32_t)g.N;
+        uint32_t oi = TE_PAD, oj = vbase * (uint32_t)H2 + (uint32_t)H;
+        if (ri >= 0) {
+          oi = (vbase + (uint32_t)ri) * (uint32_t)H2;
+          oj = (vbase + (uint32_t)rj) * (uint32_t)H2 + (uint32_t)H;
+        }
+        tab[buf * 256 + r] = oi;
+        tab[buf * 256 + 128 + r] = oj;
+      }
+    };
+    // pull the tile's rows of P towards L2 long before init_unit gathers them
+    auto prefetch_rows = [&](int buf) {
+      if (warp < 8) {
+        const int e = (warp * 32 + lane) >> 1;
+        const uint32_t o = tab[buf * 256 + ((lane & 1) ? 128 : 0) + e];
+        if (o != TE_PAD) {
+          const char *pp = reinterpret_cast<const char *>(g.P + o);
+#pragma unroll
+          for (int l = 0; l < 16; l++) prefetch_l2(pp + l * 128);
+        }
+      }
+    };
+    // U[c][e] = P_i[i(e)][c] + P_j[j(e)][c] for this warp's lane quarter of its unit
+    auto init_unit = [&](int buf) {
+      const uint4 *ti = reinterpret_cast<const uint4 *>(tab + buf * 256);
+      const uint4 *tj = reinterpret_cast<const uint4 *>(tab + buf * 256 + 128);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; cb++) {
+        uint32_t val[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+          const uint4 oi = ti[cb * 8 + j4], oj = tj[cb * 8 + j4];
+          const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
+          const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float a = Pc[ois[k] == TE_PAD ? 0u : ois[k]];
+            const float b = Pc[ojs[k]];
+            val[j4 * 4 + k] = __float_as_uint(a + b);
+          }
+        }
+        tmem_st32(taddr + cb * 32, val);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(acc_init(u4));
+    };
+
+    float dlt[3] = {0.f, 0.f, 0.f}, dlt_next[3] = {0.f, 0.f, 0.f};
+    uint32_t it = 0;
+    // prologue: tables + accumulator init of the first item
+    load_tables(blockIdx.x, 0, dlt);
+    TE_WORKER_BARRIER();
+    init_unit(0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int buf = it & 1;
+      const int tile = item % g.n_tiles;
+      const int next = item + gridDim.x;
+      const bool has_next = next < n_items;
+      if (has_next) load_tables(next, buf ^ 1, dlt_next);
+      TE_WORKER_BARRIER();
+      if (has_next) prefetch_rows(buf ^ 1);
+      const int n = g.seg_n[tile];
+      const uint32_t *t_oi = tab + buf * 256;
+      // ---- sinusoid embedding: group u4 builds the chunks with kc % 4 == u4 into slot u4 ----
+      {
+        const bool valid = t_oi[r] != TE_PAD;
+#pragma unroll 1
+        for (int d = 0; d < 3; d++) {
+          float s1, c1, s48, c48, sk, ck;
+          sincospif(2.0f * dlt[d], &s1, &c1);
+          sincospif(96.0f * dlt[d], &s48, &c48);
+          sincospif((float)(32 * u4) * dlt[d], &sk, &ck);      // frequency 16*u4
+#pragma unroll 1
+          for (int half = 0; half < 2; half++) {                  // chunks m = u4 and u4 + 4 of this dimension
+            const uint32_t use = it * 6 + d * 2 + half;           // how often slot u4 has been used
+            mbar_wait(a_empty(u4), (use & 1) ^ 1);
+            uint8_t *slot = smem + u4 * TE_A_BYTES + r * 16;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                w[e] = valid ? pack_half2(sk, ck) : 0u;
+                const float sn = fmaf(sk, c1, ck * s1);
+                const float cn = fmaf(ck, c1, -sk * s1);
+                sk = sn; ck = cn;
+              }
+              *reinterpret_cast<uint4 *>(slot + p * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            {  // jump over the other three groups' 48 frequencies
+              const float sn = fmaf(sk, c48, ck * s48);
+              const float cn = fmaf(ck, c48, -sk * s48);
+              sk = sn; ck = cn;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(a_full(u4));
+          }
+        }
+      }
+      // ---- E1: a1 = SiLU(U), thread = channel, MN-major fp16 operand of GEMM2 ----
+      mbar_wait(acc1_full, it & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int cb = 0; cb < 4; cb++) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + cb * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            w[e] = pack_half2(silu_fast(__uint_as_float(acc[8 * p + 2 * e])),
+                              silu_fast(__uint_as_float(acc[8 * p + 2 * e + 1])));
+          *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(a1_ready);
+      // ---- E2: agg_i = mean_j SiLU(U + b2); then the unit is re-initialised for the next item ----
+      {
+        const float inv_n = 1.0f / (float)n;
+        mbar_wait(acc2_full(u4), it & 1);
+        tc_fence_after_sync();
+        float sum = 0.f;
+        int cnt = 0, seg0 = 0;   // seg0 = first edge row of the current segment
+#pragma unroll 1
+        for (int cb = 0; cb < 4; cb++) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + cb * 32, acc);
+          tmem_ld_wait();
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]) + bias);   // branch-free pass
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            sum += t[j];
+            if (++cnt == n) {
+              const uint32_t o = t_oi[seg0];
+              if (o != TE_PAD)
+                out[(int64_t)(o >> 10) * g.ld_agg] = __float2half_rn(fminf(fmaxf(sum * inv_n, -65504.f), 65504.f));
+              sum = 0.f;
+              cnt = 0;
+              seg0 += n;
+            }
+          }
+        }
+        tc_fence_before_sync();
+        if (has_next) init_unit(buf ^ 1);
+      }
+      dlt[0] = dlt_next[0]; dlt[1] = dlt_next[1]; dlt[2] = dlt_next[2];
+      // all of GEMM2 has completed (E2 of unit 3 is done) and nobody reads this item's tables any more:
+      // the a1 / embedding region and the table buffer may be overwritten
+      TE_WORKER_BARRIER();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {
+  const int n_items = a.n_tiles * a.V;
+  if (n_items == 0) return CB2_OK;
+  if ((uint64_t)a.V * (uint64_t)a.N * (uint64_t)H2 >= (1ull << 32))
+    return fail(CB2_ERR_UNSUPPORTED, "tensor-core edge kernel: V*N*1024 must fit 32 bits (shard the batch)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
+    attr_set = true;
+  }
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  k_tc_edge<<<grid, TE_THREADS, TE_SMEM, st>>>(a);
+  CB2_LAUNCH_OK("k_tc_edge");
+  return CB2_OK;
+}
+
+}  // namespace cb2

@@ -68,6 +68,7 @@ struct UpdateParams {
   int noise_mode, t_start;
   const float *rand_a, *rand_l, *rand_x, *rand_x2;
   uint64_t seed;
+  const uint64_t *seed_dev;
   const int64_t *graph_gid;
   const float *head_out;
   const float *lat_out;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) k_update_predictor(UpdateParams p) {
           float4 u = *reinterpret_cast<const float4 *>(p.rand_a + ((int64_t)s * p.N + n) * NTYPE + 4 * lane);
           u4[0] = u.x; u4[1] = u.y; u4[2] = u.z; u4[3] = u.w;
         } else {
-          U4 r = noise_block(p.seed, p.graph_gid[g], atom, t, 0, lane);
+          U4 r = noise_block(p.seed_dev ? *p.seed_dev : p.seed, p.graph_gid[g], atom, t, 0, lane);
           u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
         }
       }
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) k_update_predictor(UpdateParams p) {
       float z = 0.f;
       if (t > 1) {
         if (p.noise_mode == 0) z = p.rand_x[((int64_t)s * p.N + n) * 3 + lane];
-        else { U4 r = noise_block(p.seed, p.graph_gid[g], atom, t, 2, lane); z = normal_from(r.x, r.y); }
+        else { U4 r = noise_block(p.seed_dev ? *p.seed_dev : p.seed, p.graph_gid[g], atom, t, 2, lane); z = normal_from(r.x, r.y); }
       }
       float pxs = __fmul_rn(px, cf[5]);
       float xo = p.x[(int64_t)n * 3 + lane];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) k_update_predictor(UpdateParams p) {
       float z = 0.f;
       if (t > 1) {
         if (p.noise_mode == 0) z = p.rand_l[((int64_t)s * p.B + g) * 9 + lane];
-        else { U4 r = noise_block(p.seed, p.graph_gid[g], 1023, t, 1, lane); z = normal_from(r.x, r.y); }
+        else { U4 r = noise_block(p.seed_dev ? *p.seed_dev : p.seed, p.graph_gid[g], 1023, t, 1, lane); z = normal_from(r.x, r.y); }
       }
       z = mask ? z : 0.f;
       float lo = p.l[(int64_t)g * 9 + lane];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) k_update_corrector(UpdateParams p) {
     if (p.noise_mode == 0) z = p.rand_x2[((int64_t)s * p.N + n) * 3 + d];
     else {
       int g = p.node2graph[n];
-      U4 r = noise_block(p.seed, p.graph_gid[g], n - p.node_base[n], t, 3, d);
+      U4 r = noise_block(p.seed_dev ? *p.seed_dev : p.seed, p.graph_gid[g], n - p.node_base[n], t, 3, d);
       z = normal_from(r.x, r.y);
     }
   }
@@ -242,7 +243,7 @@ static UpdateParams make_params(const cb2_batch *b, cb2_state *s, const cb2_step
   p.one_minus_cs = (float)(1.0 - (double)a->cond_scale);
   p.noise_mode = a->noise_mode; p.t_start = a->t_start;
   p.rand_a = a->rand_a; p.rand_l = a->rand_l; p.rand_x = a->rand_x; p.rand_x2 = a->rand_x2;
-  p.seed = a->seed; p.graph_gid = a->graph_gid;
+  p.seed = a->seed; p.seed_dev = a->seed_dev; p.graph_gid = a->graph_gid;
   p.head_out = nullptr; p.lat_out = nullptr;
   return p;
 }

@@ -98,10 +98,26 @@ class SamplerRun:
         else:
             args.noise_mode, args.t_start = 1, cfg.timesteps
         args.seed = int(seed) & (2 ** 64 - 1)
+        self.seed_dev = torch.tensor([int(seed) & (2 ** 63 - 1)], dtype=torch.int64, device=dev)
+        args.seed_dev = self.seed_dev.data_ptr()
         args.graph_gid = self.graph_gid.data_ptr()
         self.args = args
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
+
+    # -- re-use of a captured run with new conditioning (pointers stay valid) -------
+    def reconfigure(self, text: Optional[torch.Tensor], null_text: Optional[torch.Tensor], seed: int,
+                    graph_gid: Optional[Sequence[int]] = None) -> None:
+        dev = self.eng.device
+        if self.text_guide:
+            text = text.to(dev, torch.float32, non_blocking=True)
+            null_text = null_text.to(dev, torch.float32, non_blocking=True)
+            if null_text.shape[0] == 1:
+                null_text = null_text.expand(self.B, -1)
+            self.text_part.copy_(self.eng.text_part(torch.cat([text, null_text], dim=0)))
+        self.seed_dev.fill_(int(seed) & (2 ** 63 - 1))
+        if graph_gid is not None:
+            self.graph_gid.copy_(torch.as_tensor(np.asarray(graph_gid, dtype=np.int64)), non_blocking=True)
 
     # -- state ---------------------------------------------------------------
     def set_state(self, a: torch.Tensor, x: torch.Tensor, l: torch.Tensor, t: int) -> None:
@@ -184,6 +200,7 @@ class ChemeleonB200:
         self.text_guide = self.cfg.text_guide
         self.use_cuda_graph = use_cuda_graph
         self.hparams = self.cfg
+        self._run_cache = {}
 
     # -- loaders (reference: chemeleon.py:97-135) ----------------------------------
     @classmethod
@@ -223,8 +240,23 @@ class ChemeleonB200:
             raise ValueError("text_guide model: text embeddings are required")
         if not self.text_guide:
             text_embeds = null_text_embeds = None
-        return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed,
-                          graph_gid, self.use_cuda_graph)
+        if noise is not None:  # parity mode: injected tensors are baked into the step arguments
+            return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed,
+                              graph_gid, self.use_cuda_graph)
+        # production mode: a captured run is re-used for every later call with the same batch
+        # shape (e.g. composition sweeps); only the conditioning, seed and sample ids change.
+        key = (tuple(int(n) for n in natoms), float(cond_scale), float(step_lr))
+        run = self._run_cache.get(key)
+        if run is None:
+            if len(self._run_cache) >= 4:
+                self._run_cache.clear()
+            run = SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, None, seed,
+                             graph_gid, self.use_cuda_graph)
+            self._run_cache[key] = run
+        else:
+            gid = graph_gid if graph_gid is not None else np.arange(run.B, dtype=np.int64)
+            run.reconfigure(text_embeds, null_text_embeds, seed, gid)
+        return run
 
     def initial_noise(self, B: int, N: int, seed: int):
         """l_T, x_T from a device generator (production mode; global order => sharding invariant)."""

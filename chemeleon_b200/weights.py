@@ -197,6 +197,13 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
     def tiled(t: Tensor) -> Optional[Tensor]:
         return d(tile_k_major(t)) if tensor_core else None
 
+    def tiled_blocks(t: Tensor, rows: int = 128) -> Optional[Tensor]:
+        """One K-major image per block of `rows` output channels (the edge kernel streams
+        W2 one 128-channel output unit at a time): [out/rows][K/8][rows][8]."""
+        if not tensor_core:
+            return None
+        return d(torch.cat([tile_k_major(t[i:i + rows]) for i in range(0, t.shape[0], rows)], dim=0))
+
     w_cond = get("decoder.film_layer.mlp_cond.0.weight")  # [1024, time_dim(+text_dim)]
     b_cond = get("decoder.film_layer.mlp_cond.0.bias")
     te = schedules.time_embedding_table(cfg.timesteps, cfg.time_dim)  # [T+1,128]
@@ -222,7 +229,7 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
             wn1=d(wn1), bn1=d(get(p + ".node_mlp.0.bias")),
             wn2=d(wn2), bn2=d(get(p + ".node_mlp.2.bias")),
             ln_g=d(get(p + ".layer_norm.weight")), ln_b=d(get(p + ".layer_norm.bias")),
-            w_hij_t=tiled(w_hij), w_fd_t=tiled(w_fd[:, perm]), w2_t=tiled(w2),
+            w_hij_t=tiled(w_hij), w_fd_t=tiled(w_fd[:, perm]), w2_t=tiled_blocks(w2),
             wn1_t=tiled(wn1), wn2_t=tiled(wn2)))
 
     A = cfg.max_atoms

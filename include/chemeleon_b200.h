@@ -158,6 +158,7 @@ typedef struct {
   const float *rand_x2;        /* [S,N,3]   normal, corrector */
   /* Philox: noise keyed by (seed, global sample id, atom, timestep, stream) */
   uint64_t seed;
+  const uint64_t *seed_dev;    /* optional device scalar overriding `seed` (lets a captured graph be re-seeded) */
   const int64_t *graph_gid;    /* [B] global sample ids (sharding-invariant noise) */
 } cb2_step_args;
 

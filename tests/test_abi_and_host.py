@@ -46,7 +46,7 @@ int main(void){
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(cb2_layer_weights), sizeof(cb2_model), sizeof(cb2_batch),
          sizeof(cb2_forward_io), sizeof(cb2_state), sizeof(cb2_step_args), offsetof(cb2_model, final_g));
   printf("%zu %zu %zu %zu\n", offsetof(cb2_batch, host_chunk_node_lo), offsetof(cb2_batch, tile_row_i),
-         offsetof(cb2_step_args, rand_a), offsetof(cb2_step_args, seed));
+         offsetof(cb2_step_args, rand_a), offsetof(cb2_step_args, graph_gid));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -59,7 +59,7 @@ int main(void){
     want = [C.sizeof(_lib.LayerWeights), C.sizeof(_lib.Model), C.sizeof(_lib.Batch), C.sizeof(_lib.ForwardIO),
             C.sizeof(_lib.State), C.sizeof(_lib.StepArgs), _lib.Model.final_g.offset,
             _lib.Batch.host_chunk_node_lo.offset, _lib.Batch.tile_row_i.offset, _lib.StepArgs.rand_a.offset,
-            _lib.StepArgs.seed.offset]
+            _lib.StepArgs.graph_gid.offset]
     assert got == want
 
 
