@@ -16,13 +16,15 @@ namespace cb2 {
 using namespace ptx;
 
 // =============================================================================================
-// k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 64 through a 4-stage ring.
+// k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 32 through a 4-stage ring
+// (96 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so that one CTA's
+// epilogue overlaps the other's main loop).
 //   warps 0-3: load the A chunk (fp16 row-major global -> canonical smem), later the epilogue
 //   warp 4   : TMEM alloc, MMA issue (one lane)
 // =============================================================================================
-constexpr int TL_BM = 128, TL_NB = 256, TL_KC = 64, TL_STAGES = 4;
-constexpr int TL_A_BYTES = TL_BM * TL_KC * 2;   // 16 KB
-constexpr int TL_W_BYTES = TL_NB * TL_KC * 2;   // 32 KB
+constexpr int TL_BM = 128, TL_NB = 256, TL_KC = 32, TL_STAGES = 4;
+constexpr int TL_A_BYTES = TL_BM * TL_KC * 2;   // 8 KB
+constexpr int TL_W_BYTES = TL_NB * TL_KC * 2;   // 16 KB
 constexpr int TL_STAGE_BYTES = TL_A_BYTES + TL_W_BYTES;
 constexpr int TL_SMEM = TL_STAGES * TL_STAGE_BYTES + 1024;
 
@@ -46,7 +48,7 @@ struct TcLinearArgs {
   int gmod, gcols, gld;
 };
 
-__global__ void __launch_bounds__(160, 1) k_tc_linear(TcLinearArgs g) {
+__global__ void __launch_bounds__(160, 2) k_tc_linear(TcLinearArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_base = sbase + TL_STAGES * TL_STAGE_BYTES;
@@ -96,12 +98,12 @@ __global__ void __launch_bounds__(160, 1) k_tc_linear(TcLinearArgs g) {
           bulk_g2s(w_s + k8 * (TL_NB * 16), src, TL_NB * 16, full_bar(s));
         }
       }
-      uint4 v[8];
+      uint4 v[TL_KC / 8];
 #pragma unroll
-      for (int k8 = 0; k8 < 8; k8++)
+      for (int k8 = 0; k8 < TL_KC / 8; k8++)
         v[k8] = valid ? *reinterpret_cast<const uint4 *>(arow + kc * TL_KC + k8 * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int k8 = 0; k8 < 8; k8++)
+      for (int k8 = 0; k8 < TL_KC / 8; k8++)
         *reinterpret_cast<uint4 *>(smem + s * TL_STAGE_BYTES + k8 * (TL_BM * 16) + r * 16) = v[k8];
       fence_proxy_async_smem();
       mbar_arrive(full_bar(s));
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_linear(TcLinearArgs g) {
 int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
   if (a.M == 0) return CB2_OK;
   if (a.K % TL_KC != 0 || a.Nw % TL_NB != 0 || (a.lda % 8) != 0)
-    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, lda%8 must be 0");
+    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%32, N%256, lda%8 must be 0");
   static bool attr_set = false;
   if (!attr_set) {
     CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));

@@ -44,6 +44,62 @@ static_assert(TE_SMEM <= 232448, "shared memory budget");
 
 __host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
 
+// ---- E2 body: mean over the n edges of each segment of SiLU(U + b2) for one TMEM unit ----
+// Segment boundaries are compile-time for N > 0 (no branches in the running sum); N == 0 is
+// the generic runtime-n version used for segment lengths without a specialisation.
+__device__ __forceinline__ void e2_store(const uint32_t *t_oi, int seg0, __half *out, int64_t ld_agg, float mean) {
+  const uint32_t o = t_oi[seg0];
+  if (o != TE_PAD) out[(int64_t)(o >> 10) * ld_agg] = __float2half_rn(fminf(fmaxf(mean, -65504.f), 65504.f));
+}
+
+template <int N>
+__device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
+                                     int64_t ld_agg) {
+  const int n = N > 0 ? N : n_rt;
+  const float inv_n = 1.0f / (float)n;
+  float sum = 0.f;
+  int cnt = 0, seg0 = 0;
+#pragma unroll
+  for (int cb = 0; cb < 4; cb++) {
+    uint32_t acc[32];
+    tmem_ld32(taddr + cb * 32, acc);
+    tmem_ld_wait();
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]) + bias);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      sum += t[j];
+      if (N > 0) {
+        if ((cb * 32 + j + 1) % (N > 0 ? N : 1) == 0) {
+          e2_store(t_oi, cb * 32 + j + 1 - N, out, ld_agg, sum * inv_n);
+          sum = 0.f;
+        }
+      } else if (++cnt == n) {
+        e2_store(t_oi, seg0, out, ld_agg, sum * inv_n);
+        sum = 0.f;
+        cnt = 0;
+        seg0 += n;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
+                                            int64_t ld_agg) {
+  switch (n) {
+#define CB2_E2_CASE(N) case N: e2_unit<N>(n, taddr, bias, t_oi, out, ld_agg); break;
+    CB2_E2_CASE(1) CB2_E2_CASE(2) CB2_E2_CASE(3) CB2_E2_CASE(4) CB2_E2_CASE(5) CB2_E2_CASE(6) CB2_E2_CASE(7)
+    CB2_E2_CASE(8) CB2_E2_CASE(9) CB2_E2_CASE(10) CB2_E2_CASE(11) CB2_E2_CASE(12) CB2_E2_CASE(13) CB2_E2_CASE(14)
+    CB2_E2_CASE(15) CB2_E2_CASE(16) CB2_E2_CASE(17) CB2_E2_CASE(18) CB2_E2_CASE(19) CB2_E2_CASE(20) CB2_E2_CASE(21)
+    CB2_E2_CASE(22) CB2_E2_CASE(23) CB2_E2_CASE(24) CB2_E2_CASE(25) CB2_E2_CASE(26) CB2_E2_CASE(27) CB2_E2_CASE(28)
+    CB2_E2_CASE(29) CB2_E2_CASE(30) CB2_E2_CASE(31) CB2_E2_CASE(32) CB2_E2_CASE(33) CB2_E2_CASE(34) CB2_E2_CASE(35)
+    CB2_E2_CASE(36) CB2_E2_CASE(37) CB2_E2_CASE(38) CB2_E2_CASE(39) CB2_E2_CASE(40)
+#undef CB2_E2_CASE
+    default: e2_unit<0>(n, taddr, bias, t_oi, out, ld_agg); break;
+  }
+}
+
 #define TE_WORKER_BARRIER() asm volatile("bar.sync 1, 512;" ::: "memory")
 
 __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
@@ -289,32 +345,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       mbar_arrive(a1_ready);
       // ---- E2: agg_i = mean_j SiLU(U + b2); then the unit is re-initialised for the next item ----
       {
-        const float inv_n = 1.0f / (float)n;
         mbar_wait(acc2_full(u4), it & 1);
         tc_fence_after_sync();
-        float sum = 0.f;
-        int cnt = 0, seg0 = 0;   // seg0 = first edge row of the current segment
-#pragma unroll 1
-        for (int cb = 0; cb < 4; cb++) {
-          uint32_t acc[32];
-          tmem_ld32(taddr + cb * 32, acc);
-          tmem_ld_wait();
-          float t[32];
-#pragma unroll
-          for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]) + bias);   // branch-free pass
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            sum += t[j];
-            if (++cnt == n) {
-              const uint32_t o = t_oi[seg0];
-              if (o != TE_PAD)
-                out[(int64_t)(o >> 10) * g.ld_agg] = __float2half_rn(fminf(fmaxf(sum * inv_n, -65504.f), 65504.f));
-              sum = 0.f;
-              cnt = 0;
-              seg0 += n;
-            }
-          }
-        }
+        e2_dispatch(n, taddr, bias, t_oi, out, g.ld_agg);
         tc_fence_before_sync();
         if (has_next) init_unit(buf ^ 1);
       }
