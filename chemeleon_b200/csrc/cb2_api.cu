@@ -43,6 +43,7 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
                       cudaStream_t st);
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
                      int64_t ldc, int64_t M, int K, int silu, cudaStream_t st);
+int debug_edge_timeline(long long *out96);
 int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
                   int64_t ld_agg, int agg_col, cudaStream_t st);
 
@@ -203,6 +204,9 @@ int cb2_abi_version(void) { return CB2_ABI_VERSION; }
 const char *cb2_last_error(void) { return g_err.c_str(); }
 
 uint64_t cb2_launch_count(void) { return g_launches.load(); }
+
+/* development aid (not part of the documented ABI): clock64 timeline of the edge kernel's CTA 0 */
+int cb2_debug_edge_timeline(long long *out96) { return debug_edge_timeline(out96); }
 
 int cb2_check_device(int device) {
   cudaDeviceProp prop;

@@ -26,23 +26,37 @@ namespace cb2 {
 using namespace ptx;
 
 constexpr int TE_KC = 32;                       // K per GEMM1 pipeline stage
-constexpr int TE_WSTAGES = 3;
+constexpr int TE_WSTAGES = 3;                   // weight ring R1 (always available)
+constexpr int TE_WEXTRA = 2;                    // two more stages inside the a1 region, usable during GEMM1 only
+constexpr int TE_WEXTRA_OFF = 65536;            // ... placed after the embedding ring
 constexpr int TE_W_BYTES = 32768;               // GEMM1: [4 k8][512 ch][16 B]; GEMM2: [16 k8][128 ch][16 B]
-constexpr int TE_ASLOTS = 4;                    // one slot per embedding group
+constexpr int TE_ASLOTS = 8;                    // two slots per embedding group
 constexpr int TE_A_BYTES = 128 * TE_KC * 2;     // 8 KB: [4 k8][128 edges][16 B]
 constexpr int TE_AREGION = 128 * H * 2;         // 128 KB: a1, MN-major [64 k8][16 e8][8 k][8 e]
 constexpr int TE_W_OFF = TE_AREGION;
 constexpr int TE_BAR_OFF = TE_W_OFF + TE_WSTAGES * TE_W_BYTES;
-constexpr int TE_TAB_OFF = TE_BAR_OFF + 256;    // 2 buffers x (off_i[128], off_j[128]) uint32
+constexpr int TE_TAB_OFF = TE_BAR_OFF + 320;    // 2 buffers x (off_i[128], off_j[128]) uint32
 constexpr int TE_SMEM = TE_TAB_OFF + 2 * 1024;
 constexpr int TE_WORKERS = 512;
-constexpr int TE_THREADS = TE_WORKERS + 64;
+constexpr int TE_NISSUE = 3;                    // MMA-issuing threads (warps 16..18), loader = warp 19
+constexpr int TE_THREADS = TE_WORKERS + 32 * (TE_NISSUE + 1);
+
 constexpr int TE_NCH1 = DIS / TE_KC;            // 24 stages of K=32
 constexpr int TE_NCH2 = 4;                      // per output unit: 4 stages of K=128
 constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
 static_assert(TE_SMEM <= 232448, "shared memory budget");
+static_assert(TE_NCH2 >= TE_NISSUE, "every issuer must own a stage of every output unit");
 
 __host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
+
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 // ---- E2 body: mean over the n edges of each segment of SiLU(U + b2) for one TMEM unit ----
 // Segment boundaries are compile-time for N > 0 (no branches in the running sum); N == 0 is
@@ -66,7 +80,7 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
     tmem_ld_wait();
     float t[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]) + bias);
+    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       sum += t[j];
@@ -100,29 +114,123 @@ __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, c
   }
 }
 
+// ---- accumulator init: U[c][e] = P_i[i(e)][c] + P_j[j(e)][c] for one lane quarter of a unit ----
+// N > 0: the tile's segment structure is compile-time, so each thread loads P_i once per
+// segment and the N rows of P_j once per crystal (they repeat for every segment of the same
+// crystal) instead of two values per edge.  N == 0: generic version, two gathers per edge.
+template <int N>
+__device__ __noinline__ void init_unit_t(uint32_t taddr, const float *Pc, const uint32_t *t_oi,
+                                         const uint32_t *t_oj) {
+  if constexpr (N == 0) {
+    const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
+    const uint4 *tj = reinterpret_cast<const uint4 *>(t_oj);
+#pragma unroll 1
+    for (int cb = 0; cb < 4; cb++) {
+      uint32_t val[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; j4++) {
+        const uint4 oi = ti[cb * 8 + j4], oj = tj[cb * 8 + j4];
+        const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
+        const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          val[j4 * 4 + k] = __float_as_uint(Pc[ois[k] == TE_PAD ? 0u : ois[k]] + Pc[ojs[k]]);
+      }
+      tmem_st32(taddr + cb * 32, val);
+    }
+  } else {
+    constexpr int S = 128 / N;
+    float piv[S];
+#pragma unroll
+    for (int sgm = 0; sgm < S; sgm++) {
+      const uint32_t oi = t_oi[sgm * N];
+      piv[sgm] = Pc[oi == TE_PAD ? 0u : oi];
+    }
+    float pj[N];
+    uint32_t cur = t_oj[0];
+#pragma unroll
+    for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) {
+      uint32_t val[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int e = cb * 32 + j;
+        if (e < S * N) {
+          if (e % N == 0 && e > 0) {            // segment start: same crystal as before?
+            const uint32_t oj0 = t_oj[e];
+            if (oj0 != cur) {
+              cur = oj0;
+#pragma unroll
+              for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
+            }
+          }
+          val[j] = __float_as_uint(piv[e / N] + pj[e % N]);
+        } else {
+          val[j] = 0u;
+        }
+      }
+      tmem_st32(taddr + cb * 32, val);
+    }
+  }
+}
+
+__device__ __forceinline__ void init_dispatch(int n, uint32_t taddr, const float *Pc, const uint32_t *t_oi,
+                                              const uint32_t *t_oj) {
+  switch (n) {
+#define CB2_INIT_CASE(N) case N: init_unit_t<N>(taddr, Pc, t_oi, t_oj); break;
+    CB2_INIT_CASE(4) CB2_INIT_CASE(5) CB2_INIT_CASE(6) CB2_INIT_CASE(7)
+    CB2_INIT_CASE(8) CB2_INIT_CASE(9) CB2_INIT_CASE(10) CB2_INIT_CASE(11) CB2_INIT_CASE(12) CB2_INIT_CASE(13)
+    CB2_INIT_CASE(14) CB2_INIT_CASE(15) CB2_INIT_CASE(16) CB2_INIT_CASE(17) CB2_INIT_CASE(18) CB2_INIT_CASE(19)
+    CB2_INIT_CASE(20) CB2_INIT_CASE(21) CB2_INIT_CASE(22) CB2_INIT_CASE(23) CB2_INIT_CASE(24) CB2_INIT_CASE(25)
+    CB2_INIT_CASE(26) CB2_INIT_CASE(27) CB2_INIT_CASE(28) CB2_INIT_CASE(29) CB2_INIT_CASE(30) CB2_INIT_CASE(31)
+    CB2_INIT_CASE(32) CB2_INIT_CASE(33) CB2_INIT_CASE(34) CB2_INIT_CASE(35) CB2_INIT_CASE(36) CB2_INIT_CASE(37)
+    CB2_INIT_CASE(38) CB2_INIT_CASE(39) CB2_INIT_CASE(40)
+#undef CB2_INIT_CASE
+    default: init_unit_t<0>(taddr, Pc, t_oi, t_oj); break;
+  }
+}
+
 #define TE_WORKER_BARRIER() asm volatile("bar.sync 1, 512;" ::: "memory")
+
+// development aid: timeline of CTA 0's items 1..3 (clock64 stamps), read back by cb2_debug_edge_timeline()
+__device__ long long g_edge_dbg[3 * 96];
+#ifdef CB2_EDGE_TIMELINE
+#define TE_STAMP(slot)                                                      \
+  do {                                                                      \
+    if (blockIdx.x == 0 && it >= 1 && it <= 3) g_edge_dbg[(it - 1) * 96 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TE_STAMP(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + TE_BAR_OFF;
-  auto a_full = [&](int s) { return bars + 8 * s; };
-  auto a_empty = [&](int s) { return bars + 32 + 8 * s; };
-  auto w_full = [&](int s) { return bars + 64 + 8 * s; };
-  auto w_empty = [&](int s) { return bars + 96 + 8 * s; };
-  const uint32_t acc1_full = bars + 128, a1_ready = bars + 136;
-  auto acc2_full = [&](int u) { return bars + 144 + 8 * u; };
-  auto acc_init = [&](int u) { return bars + 176 + 8 * u; };
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 208);
+  auto a_full = [&](int s) { return bars + 8 * s; };            // 8
+  auto a_empty = [&](int s) { return bars + 64 + 8 * s; };      // 8
+  auto w_full = [&](int s) { return bars + 128 + 8 * s; };      // 5
+  auto w_empty = [&](int s) { return bars + 168 + 8 * s; };     // 5
+  const uint32_t acc1_full = bars + 208, a1_ready = bars + 216;
+  auto acc2_full = [&](int u) { return bars + 224 + 8 * u; };
+  auto acc_init = [&](int u) { return bars + 256 + 8 * u; };
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 288);
+  const uint32_t ready_addr = bars + 296;   // number of MMA-thread wait points the scout has cleared
+  // weight stage s: 0..2 = ring R1, 3..4 = extra stages inside the a1 region (GEMM1 only)
+  auto w_addr = [&](int s) {
+    return s < TE_WSTAGES ? sbase + TE_W_OFF + s * TE_W_BYTES : sbase + TE_WEXTRA_OFF + (s - TE_WSTAGES) * TE_W_BYTES;
+  };
   uint32_t *tab = reinterpret_cast<uint32_t *>(smem + TE_TAB_OFF);   // [buf][0: off_i, 1: off_j][128]
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   if (tid == 0) {
     for (int s = 0; s < TE_ASLOTS; s++) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < TE_WSTAGES; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    mbar_init(acc1_full, 1);
+    for (int s = 0; s < TE_WSTAGES + TE_WEXTRA; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    *reinterpret_cast<volatile uint32_t *>(smem + TE_BAR_OFF + 296) = 0u;
+    mbar_init(acc1_full, TE_NISSUE);
     mbar_init(a1_ready, TE_WORKERS);
-    for (int u = 0; u < 4; u++) { mbar_init(acc2_full(u), 1); mbar_init(acc_init(u), 128); }
+    for (int u = 0; u < 4; u++) { mbar_init(acc2_full(u), TE_NISSUE); mbar_init(acc_init(u), 128); }
     fence_barrier_init();
   }
   if (warp == 16) {
@@ -135,68 +243,101 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
   const uint32_t tmem = *tmem_slot;
   const int n_items = g.n_tiles * g.V;
 
-  if (warp == 17) {
+  if (warp == 16 + TE_NISSUE) {
     // ------------------------------ weight loader ------------------------------
     if (lane == 0) {
-      uint32_t wc = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int c = 0; c < TE_NCH1 + 4 * TE_NCH2; c++, wc++) {
-          const int s = wc % TE_WSTAGES;
-          mbar_wait(w_empty(s), ((wc / TE_WSTAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(w_full(s), TE_W_BYTES);
-          const __half *src = (c < TE_NCH1) ? g.w_fd_t + (int64_t)c * (TE_W_BYTES / 2)
-                                            : g.w2_t + (int64_t)(c - TE_NCH1) * (TE_W_BYTES / 2);
-          bulk_g2s(sbase + TE_W_OFF + s * TE_W_BYTES, src, TE_W_BYTES, w_full(s));
+      uint32_t use[TE_WSTAGES + TE_WEXTRA] = {0, 0, 0, 0, 0};
+      uint32_t it = 0;
+      auto load_stage = [&](int st, const __half *src) {
+        mbar_wait(w_empty(st), (use[st] & 1) ^ 1);
+        mbar_arrive_expect_tx(w_full(st), TE_W_BYTES);
+        bulk_g2s(w_addr(st), src, TE_W_BYTES, w_full(st));
+        use[st]++;
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        bool a1_dead = (it == 0);
+#pragma unroll
+        for (int kc = 0; kc < TE_NCH1; kc++) {       // GEMM1: five stages
+          const int st = kc % (TE_WSTAGES + TE_WEXTRA);
+          if (st >= TE_WSTAGES && !a1_dead) {         // the extra stages alias a1 of the previous item
+            mbar_wait(acc2_full(3), (it - 1) & 1);
+            a1_dead = true;
+          }
+          load_stage(st, g.w_fd_t + (int64_t)kc * (TE_W_BYTES / 2));
         }
+#pragma unroll
+        for (int c2 = 0; c2 < 4 * TE_NCH2; c2++)     // GEMM2: ring R1 only
+          load_stage(c2 % TE_WSTAGES, g.w2_t + (int64_t)c2 * (TE_W_BYTES / 2));
       }
     }
-  } else if (warp == 16) {
-    // ------------------------------ MMA issuer ------------------------------
+  } else if (warp >= 16 && warp < 16 + TE_NISSUE) {
+    // ------------------------------ MMA issuers ------------------------------
+    // Any synchronisation point in an issuing thread (an mbarrier wait, even a plain shared-memory
+    // poll) idles the tensor pipe for ~170 cycles because only ~2 MMAs are queued ahead (measured
+    // with scripts/mma_bench.cu: 8 MMAs + 2 waits = 976 cycles instead of 512).  Three threads
+    // therefore issue alternate K chunks: while one waits, the others' MMAs keep the pipe busy.
+    // All MMAs accumulate (the units are pre-loaded), so their relative order is irrelevant.
     if (lane == 0) {
+      const int ii = warp - 16;
       constexpr uint32_t idesc_kk = idesc_f16_f32(128, 128);
       constexpr uint32_t idesc_kmn = idesc_b_mn(idesc_f16_f32(128, 128));
-      uint32_t wc = 0, ac = 0, it = 0;
+      constexpr int NS = TE_WSTAGES + TE_WEXTRA;
+      uint32_t it = 0;
+      // descriptors = base (LBO/SBO/version fields + smem base) + (byte offset >> 4) in the low word
+      const uint64_t d_lbo2k = smem_desc_kmajor(sbase, 2048, 128);   // emb slots, a1, W2 stages
+      const uint64_t d_lbo8k = smem_desc_kmajor(sbase, 8192, 128);   // W_fd stages
+      auto w_off = [](int st) { return st < TE_WSTAGES ? TE_W_OFF + st * TE_W_BYTES : TE_WEXTRA_OFF + (st - TE_WSTAGES) * TE_W_BYTES; };
+      // uses of weight stage st per item: GEMM1 chunk kc uses stage kc % 5, GEMM2 stage c2 uses c2 % 3
+      auto uses_per_item = [](int st) { return st == 0 ? 11u : st < 3 ? 10u : st == 3 ? 5u : 4u; };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        for (int u = 0; u < 4; u++) mbar_wait(acc_init(u), it & 1);   // units hold P_i + P_j
+        if (ii == 0) TE_STAMP(0);
+        for (int u = 0; u < 4; u++) mbar_wait(acc_init(u), it & 1);   // the units hold P_i + P_j
         tc_fence_after_sync();
+        if (ii == 0) TE_STAMP(1);
         // GEMM1: U_m += W_fd[m] emb^T, all four units per K chunk
-        for (int kc = 0; kc < TE_NCH1; kc++, wc++, ac++) {
-          const int as = ac % TE_ASLOTS, ws = wc % TE_WSTAGES;
-          mbar_wait(a_full(as), (ac / TE_ASLOTS) & 1);
-          mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
+#pragma unroll
+        for (int kc = 0; kc < TE_NCH1; kc++) {
+          if (kc % TE_NISSUE != ii) continue;
+          const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
+          mbar_wait(a_full(as), (it * 3 + (kc >> 3)) & 1);
+          mbar_wait(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
           tc_fence_after_sync();
-          const uint32_t e_s = sbase + as * TE_A_BYTES, w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
 #pragma unroll
           for (int j = 0; j < 2; j++) {
-            const uint64_t bd = smem_desc_kmajor(e_s + 2 * j * 2048, 2048, 128);
+            const uint64_t bd = d_lbo2k + (uint64_t)((as * TE_A_BYTES + 2 * j * 2048) >> 4);
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-              const uint64_t ad = smem_desc_kmajor(w_s + 2 * j * 8192 + m * 2048, 8192, 128);
+              const uint64_t ad = d_lbo8k + (uint64_t)((w_off(ws) + 2 * j * 8192 + m * 2048) >> 4);
               umma_f16(tmem + m * 128, ad, bd, idesc_kk, 1u);
             }
           }
           umma_commit(a_empty(as));
           umma_commit(w_empty(ws));
         }
-        umma_commit(acc1_full);
-        // GEMM2: U_m' = W2[m'] a1^T, unit after unit
+        umma_commit(acc1_full);          // count TE_NISSUE: complete when every issuer's GEMM1 MMAs are done
+        if (ii == 0) TE_STAMP(2);
+        // GEMM2: U_m' += W2[m'] a1^T (units pre-loaded with b2), unit after unit
         mbar_wait(a1_ready, it & 1);
         tc_fence_after_sync();
-        for (int u = 0; u < 4; u++) {
-          for (int kc = 0; kc < TE_NCH2; kc++, wc++) {
-            const int ws = wc % TE_WSTAGES;
-            mbar_wait(w_full(ws), (wc / TE_WSTAGES) & 1);
-            tc_fence_after_sync();
-            const uint32_t w_s = sbase + TE_W_OFF + ws * TE_W_BYTES;
+        if (ii == 0) TE_STAMP(3);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const uint64_t ad = smem_desc_kmajor(w_s + 2 * j * 2048, 2048, 128);
-              const uint64_t bd = smem_desc_kmajor(sbase + (kc * 16 + 2 * j) * 2048, 2048, 128);
-              umma_f16(tmem + u * 128, ad, bd, idesc_kmn, (kc > 0 || j > 0) ? 1u : 0u);
-            }
-            umma_commit(w_empty(ws));
+        for (int c2 = 0; c2 < 4 * TE_NCH2; c2++) {
+          if (c2 % TE_NISSUE != ii) continue;
+          const int u = c2 / TE_NCH2, kc = c2 % TE_NCH2, ws = c2 % TE_WSTAGES;
+          mbar_wait(w_full(ws), (it * uses_per_item(ws) + 5 + c2 / TE_WSTAGES) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint64_t ad = d_lbo2k + (uint64_t)((w_off(ws) + 2 * j * 2048) >> 4);
+            const uint64_t bd = d_lbo2k + (uint64_t)(((kc * 16 + 2 * j) * 2048) >> 4);
+            umma_f16(tmem + u * 128, ad, bd, idesc_kmn, 1u);
           }
-          umma_commit(acc2_full(u));
+          umma_commit(w_empty(ws));
+          // last stage of this issuer within unit u -> its share of "unit u complete"
+          if (c2 + TE_NISSUE >= (u + 1) * TE_NCH2) {
+            umma_commit(acc2_full(u));
+            if (c2 == (u + 1) * TE_NCH2 - 1) TE_STAMP(4 + u);
+          }
         }
       }
     }
@@ -245,26 +386,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       }
     };
     // U[c][e] = P_i[i(e)][c] + P_j[j(e)][c] for this warp's lane quarter of its unit
-    auto init_unit = [&](int buf) {
-      const uint4 *ti = reinterpret_cast<const uint4 *>(tab + buf * 256);
-      const uint4 *tj = reinterpret_cast<const uint4 *>(tab + buf * 256 + 128);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; cb++) {
-        uint32_t val[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-          const uint4 oi = ti[cb * 8 + j4], oj = tj[cb * 8 + j4];
-          const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
-          const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float a = Pc[ois[k] == TE_PAD ? 0u : ois[k]];
-            const float b = Pc[ojs[k]];
-            val[j4 * 4 + k] = __float_as_uint(a + b);
-          }
-        }
-        tmem_st32(taddr + cb * 32, val);
-      }
+    auto init_unit = [&](int buf, int n_tile) {
+      init_dispatch(n_tile, taddr, Pc, tab + buf * 256, tab + buf * 256 + 128);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(acc_init(u4));
@@ -275,7 +398,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     // prologue: tables + accumulator init of the first item
     load_tables(blockIdx.x, 0, dlt);
     TE_WORKER_BARRIER();
-    init_unit(0);
+    init_unit(0, g.seg_n[blockIdx.x % g.n_tiles]);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
       const int buf = it & 1;
       const int tile = item % g.n_tiles;
@@ -297,9 +420,12 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
           sincospif((float)(32 * u4) * dlt[d], &sk, &ck);      // frequency 16*u4
 #pragma unroll 1
           for (int half = 0; half < 2; half++) {                  // chunks m = u4 and u4 + 4 of this dimension
-            const uint32_t use = it * 6 + d * 2 + half;           // how often slot u4 has been used
-            mbar_wait(a_empty(u4), (use & 1) ^ 1);
-            uint8_t *slot = smem + u4 * TE_A_BYTES + r * 16;
+            const int cidx = d * 2 + half;                        // this group's chunk number within the item
+            const int as = u4 + 4 * (cidx & 1);                   // two slots per group, used alternately
+            const uint32_t use = it * 3 + (cidx >> 1);            // how often slot `as` has been used
+            mbar_wait(a_empty(as), (use & 1) ^ 1);
+            if (tid == 0) TE_STAMP(32 + 2 * cidx);
+            uint8_t *slot = smem + as * TE_A_BYTES + r * 16;
 #pragma unroll
             for (int p = 0; p < 4; p++) {
               uint32_t w[4];
@@ -318,13 +444,16 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
               sk = sn; ck = cn;
             }
             fence_proxy_async_smem();
-            mbar_arrive(a_full(u4));
+            mbar_arrive(a_full(as));
+            if (tid == 0) TE_STAMP(33 + 2 * cidx);
           }
         }
       }
       // ---- E1: a1 = SiLU(U), thread = channel, MN-major fp16 operand of GEMM2 ----
+      if (tid == 0) TE_STAMP(8);
       mbar_wait(acc1_full, it & 1);
       tc_fence_after_sync();
+      if (tid == 0) TE_STAMP(9);
 #pragma unroll 1
       for (int cb = 0; cb < 4; cb++) {
         uint32_t acc[32];
@@ -340,16 +469,28 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
           *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      {  // pre-load the unit with b2: every GEMM2 MMA accumulates, so the issuers need no ordering
+        uint32_t bv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) bv[j] = __float_as_uint(bias);
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) tmem_st32(taddr + cb * 32, bv);
+        tmem_st_wait();
+      }
       tc_fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(a1_ready);
+      if (tid == 0) TE_STAMP(10);
       // ---- E2: agg_i = mean_j SiLU(U + b2); then the unit is re-initialised for the next item ----
       {
         mbar_wait(acc2_full(u4), it & 1);
         tc_fence_after_sync();
+        if (lane == 0 && q == 0) TE_STAMP(11 + 4 * u4);
         e2_dispatch(n, taddr, bias, t_oi, out, g.ld_agg);
+        if (lane == 0 && q == 0) TE_STAMP(12 + 4 * u4);
         tc_fence_before_sync();
-        if (has_next) init_unit(buf ^ 1);
+        if (has_next) init_unit(buf ^ 1, g.seg_n[next % g.n_tiles]);
+        if (lane == 0 && q == 0) TE_STAMP(13 + 4 * u4);
       }
       dlt[0] = dlt_next[0]; dlt[1] = dlt_next[1]; dlt[2] = dlt_next[2];
       // all of GEMM2 has completed (E2 of unit 3 is done) and nobody reads this item's tables any more:
@@ -360,6 +501,11 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+int debug_edge_timeline(long long *out96) {
+  CB2_CUDA_OK(cudaMemcpyFromSymbol(out96, g_edge_dbg, sizeof(long long) * 3 * 96));
+  return CB2_OK;
 }
 
 int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {

@@ -29,3 +29,20 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 fl = 2 * topo.E * 1310720
 print(f"edge layer B={B} n={n}: {ms:.3f} ms/launch  {fl/ms/1e9:.1f} TFLOP/s  tiles={topo.n_tiles}")
+if os.environ.get("CB2_TIMELINE"):
+    import numpy as np
+    buf = (C.c_longlong * 288)()
+    eng.lib.cb2_debug_edge_timeline.argtypes = [C.c_void_p]
+    eng.lib.cb2_debug_edge_timeline(buf)
+    a = np.array(buf[:]).reshape(3, 96)
+    names = {0: "mma:top", 1: "mma:acc_init ok", 2: "mma:G1 issued", 3: "mma:a1_ready ok", 4: "mma:G2(0) issued", 5: "G2(1)", 6: "G2(2)", 7: "G2(3)",
+             8: "w0:emb done", 9: "w0:acc1_full ok", 10: "w0:E1 done", 11: "u0:acc2_full ok", 12: "u0:E2 done", 13: "u0:init done",
+             15: "u1:acc2 ok", 16: "u1:E2 done", 17: "u1:init done", 19: "u2:acc2 ok", 20: "u2:E2 done", 21: "u2:init done",
+             23: "u3:acc2 ok", 24: "u3:E2 done", 25: "u3:init done"}
+    for itx in range(3):
+        base = a[itx, 0]
+        ev = sorted((int(a[itx, k] - base), names[k]) for k in names if a[itx, k] != 0)
+        print("item", itx + 1, " | ".join(f"{n}@{t}" for t, n in ev))
+        print("   producer g0 (slot free, chunk published):", [int(a[itx, 32 + k] - base) for k in range(12)])
+        print("   mma chunk start times:", [int(a[itx, 48 + k] - base) for k in range(24)])
+
