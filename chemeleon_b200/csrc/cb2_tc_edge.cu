@@ -352,22 +352,28 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     __half *out = g.agg16 + g.agg_col + c;
     uint8_t *a1_dst = smem + (size_t)(c / 8) * 2048 + (c % 8) * 16;
 
-    // row tables of one tile -> buffer `buf` (group 0 writes them); every thread keeps the
-    // fractional-coordinate difference of its row in registers
-    auto load_tables = [&](int item, int buf, float (&dl)[3]) {
-      const int tile = item % g.n_tiles, v = item / g.n_tiles;
-      const int ri = g.row_i[(int64_t)tile * 128 + r], rj = g.row_j[(int64_t)tile * 128 + r];
+    // The (i, j) node ids of this thread's edge row are fetched one item ahead (fetch_rows); the
+    // tile tables (group 0 writes them) and the fractional-coordinate difference follow half an
+    // item later (publish_rows), so that no global-load latency sits on the critical path.
+    int ri_p = -1, rj_p = 0;
+    auto fetch_rows = [&](int item) {
+      const int tile = item % g.n_tiles;
+      ri_p = g.row_i[(int64_t)tile * 128 + r];
+      rj_p = g.row_j[(int64_t)tile * 128 + r];
+    };
+    auto publish_rows = [&](int item, int buf, float (&dl)[3]) {
+      const int v = item / g.n_tiles;
       dl[0] = dl[1] = dl[2] = 0.f;
-      if (ri >= 0) {
+      if (ri_p >= 0) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) dl[d] = g.x[(int64_t)rj * 3 + d] - g.x[(int64_t)ri * 3 + d];
+        for (int d = 0; d < 3; d++) dl[d] = g.x[(int64_t)rj_p * 3 + d] - g.x[(int64_t)ri_p * 3 + d];
       }
       if (u4 == 0) {
         const uint32_t vbase = (uint32_t)v * (uint32_t)g.N;
         uint32_t oi = TE_PAD, oj = vbase * (uint32_t)H2 + (uint32_t)H;
-        if (ri >= 0) {
-          oi = (vbase + (uint32_t)ri) * (uint32_t)H2;
-          oj = (vbase + (uint32_t)rj) * (uint32_t)H2 + (uint32_t)H;
+        if (ri_p >= 0) {
+          oi = (vbase + (uint32_t)ri_p) * (uint32_t)H2;
+          oj = (vbase + (uint32_t)rj_p) * (uint32_t)H2 + (uint32_t)H;
         }
         tab[buf * 256 + r] = oi;
         tab[buf * 256 + 128 + r] = oj;
@@ -395,18 +401,19 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
 
     float dlt[3] = {0.f, 0.f, 0.f}, dlt_next[3] = {0.f, 0.f, 0.f};
     uint32_t it = 0;
-    // prologue: tables + accumulator init of the first item
-    load_tables(blockIdx.x, 0, dlt);
+    // prologue: tables + accumulator init of the first item, row ids of the second
+    fetch_rows(blockIdx.x);
+    publish_rows(blockIdx.x, 0, dlt);
     TE_WORKER_BARRIER();
     init_unit(0, g.seg_n[blockIdx.x % g.n_tiles]);
+    if ((int)(blockIdx.x + gridDim.x) < n_items) fetch_rows(blockIdx.x + gridDim.x);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
       const int buf = it & 1;
       const int tile = item % g.n_tiles;
       const int next = item + gridDim.x;
       const bool has_next = next < n_items;
-      if (has_next) load_tables(next, buf ^ 1, dlt_next);
-      TE_WORKER_BARRIER();
-      if (has_next) prefetch_rows(buf ^ 1);
+      // the embedding ring aliases a1 of the previous item: all of its GEMM2 must have completed
+      if (it > 0) mbar_wait(acc2_full(3), (it - 1) & 1);
       const int n = g.seg_n[tile];
       const uint32_t *t_oi = tab + buf * 256;
       // ---- sinusoid embedding: group u4 builds the chunks with kc % 4 == u4 into slot u4 ----
@@ -449,6 +456,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
           }
         }
       }
+      // every group has finished the previous item (its tables are dead): publish the next item's
+      TE_WORKER_BARRIER();
+      if (has_next) publish_rows(next, buf ^ 1, dlt_next);
       // ---- E1: a1 = SiLU(U), thread = channel, MN-major fp16 operand of GEMM2 ----
       if (tid == 0) TE_STAMP(8);
       mbar_wait(acc1_full, it & 1);
@@ -481,6 +491,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       fence_proxy_async_smem();
       mbar_arrive(a1_ready);
       if (tid == 0) TE_STAMP(10);
+      TE_WORKER_BARRIER();                         // the next item's tables are visible to everybody
+      if (has_next) prefetch_rows(buf ^ 1);
+      if (next + (int)gridDim.x < n_items) fetch_rows(next + gridDim.x);
       // ---- E2: agg_i = mean_j SiLU(U + b2); then the unit is re-initialised for the next item ----
       {
         mbar_wait(acc2_full(u4), it & 1);
@@ -493,9 +506,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         if (lane == 0 && q == 0) TE_STAMP(13 + 4 * u4);
       }
       dlt[0] = dlt_next[0]; dlt[1] = dlt_next[1]; dlt[2] = dlt_next[2];
-      // all of GEMM2 has completed (E2 of unit 3 is done) and nobody reads this item's tables any more:
-      // the a1 / embedding region and the table buffer may be overwritten
-      TE_WORKER_BARRIER();
     }
   }
   tc_fence_before_sync();
