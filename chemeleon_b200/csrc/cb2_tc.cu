@@ -85,28 +85,42 @@ __global__ void __launch_bounds__(160, 2) k_tc_linear(TcLinearArgs g) {
     const int64_t grow = m0 + r;
     const bool valid = grow < g.M;
     const __half *arow = g.A + (valid ? grow : 0) * g.lda;
-    for (int kc = 0; kc < nk; kc++) {
-      const int s = kc % TL_STAGES;
-      mbar_wait(empty_bar(s), ((kc / TL_STAGES) & 1) ^ 1);
-      const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
-      const uint32_t w_s = a_s + TL_A_BYTES;
-      if (tid == 0) {
-        mbar_arrive_expect_tx(full_bar(s), TL_W_BYTES);
+    // the A rows are prefetched three K chunks ahead into registers (the loads of one chunk are
+    // only 64 B per thread: without the look-ahead this loop is latency-bound)
+    constexpr int PF = 3;
+    uint4 pre[PF + 1][TL_KC / 8];
+    auto gload = [&](uint4 (&dst)[TL_KC / 8], int kc) {
 #pragma unroll
-        for (int k8 = 0; k8 < TL_KC / 8; k8++) {
-          const __half *src = g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8;
-          bulk_g2s(w_s + k8 * (TL_NB * 16), src, TL_NB * 16, full_bar(s));
+      for (int k8 = 0; k8 < TL_KC / 8; k8++)
+        dst[k8] = valid ? *reinterpret_cast<const uint4 *>(arow + kc * TL_KC + k8 * 8) : make_uint4(0, 0, 0, 0);
+    };
+#pragma unroll
+    for (int u = 0; u < PF; u++)
+      if (u < nk) gload(pre[u], u);
+    for (int kc0 = 0; kc0 < nk; kc0 += PF + 1) {
+#pragma unroll
+      for (int u = 0; u <= PF; u++) {
+        const int kc = kc0 + u;
+        if (kc >= nk) break;
+        if (kc + PF < nk) gload(pre[(u + PF) % (PF + 1)], kc + PF);
+        const int s = kc % TL_STAGES;
+        mbar_wait(empty_bar(s), ((kc / TL_STAGES) & 1) ^ 1);
+        const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
+        const uint32_t w_s = a_s + TL_A_BYTES;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(s), TL_W_BYTES);
+#pragma unroll
+          for (int k8 = 0; k8 < TL_KC / 8; k8++) {
+            const __half *src = g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8;
+            bulk_g2s(w_s + k8 * (TL_NB * 16), src, TL_NB * 16, full_bar(s));
+          }
         }
+#pragma unroll
+        for (int k8 = 0; k8 < TL_KC / 8; k8++)
+          *reinterpret_cast<uint4 *>(smem + s * TL_STAGE_BYTES + k8 * (TL_BM * 16) + r * 16) = pre[u][k8];
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar(s));
       }
-      uint4 v[TL_KC / 8];
-#pragma unroll
-      for (int k8 = 0; k8 < TL_KC / 8; k8++)
-        v[k8] = valid ? *reinterpret_cast<const uint4 *>(arow + kc * TL_KC + k8 * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int k8 = 0; k8 < TL_KC / 8; k8++)
-        *reinterpret_cast<uint4 *>(smem + s * TL_STAGE_BYTES + k8 * (TL_BM * 16) + r * 16) = v[k8];
-      fence_proxy_async_smem();
-      mbar_arrive(full_bar(s));
     }
     // ---------------- epilogue ----------------
     mbar_wait(acc_bar, 0);

@@ -65,7 +65,9 @@ typedef struct {
   const float *bn2;
   const float *ln_g;    /* CSPLayer.layer_norm */
   const float *ln_b;
-  /* fp16 tcgen05 operand images [K/8][rows][8]; NULL when only exact mode is used */
+  /* fp16 tcgen05 operand images (K-major, no swizzle: [K/8][rows][8]); NULL when only exact mode is
+   * used.  w_fd_t has its K columns permuted to d*256 + 2k + {sin,cos} (weights.fd_column_order);
+   * w2_t is stored as four images of 128 output channels each: [4][64][128][8]. */
   const void *w_hij_t, *w_fd_t, *w2_t, *wn1_t, *wn2_t;
 } cb2_layer_weights;
 
@@ -185,7 +187,7 @@ int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bia
 
 /* C = act(A16 W16^T + bias) on the tensor cores (tcgen05, fp32 accumulate).  A16: fp16
  * row-major [M,lda]; Wt: fp16 operand image [K/8][Nw][8] of a torch Linear weight [Nw,K]
- * (weights.tile_k_major); K % 64 == 0, Nw % 256 == 0.  The building block of the
+ * (weights.tile_k_major); K % 32 == 0, Nw % 256 == 0.  The building block of the
  * node-level GEMMs (FilmLayer.proj, hoisted W1 blocks, node_mlp; cspnet.py:86,113,120). */
 int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
                   int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream);
