@@ -9,7 +9,7 @@ namespace cb2 {
 // x * sigmoid(x) = x / (1 + 2^(-x log2 e)) with the ftz ex2/rcp approximations: five
 // instructions, two MUFU ops, relative error ~1e-6 (the result feeds an fp16 rounding).
 // x -> -inf gives -0, x -> +inf gives x.  (A Newton reciprocal on the FMA pipe instead of
-// MUFU.RCP was measured 12 % slower: the epilogues are issue-bound, not MUFU-bound.)
+// MUFU.RCP was measured: 12 % slower when used everywhere, no gain when used in E1 only.)
 __device__ __forceinline__ float silu_fast(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
