@@ -23,7 +23,7 @@ int launch_film_cond(const float *time_table, const float *text_part, const int3
                      int64_t rows, cudaStream_t st);
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
-                      int64_t ld_hn16, int N, int B, int V, cudaStream_t st);
+                      int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
 int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *out16, int64_t rows,
                      cudaStream_t st);
 int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
@@ -45,7 +45,7 @@ int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const
                      int64_t ldc, int64_t M, int K, int silu, cudaStream_t st);
 int debug_edge_timeline(long long *out96);
 int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
-                  int64_t ld_agg, int agg_col, cudaStream_t st);
+                  int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
 
 size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) {
   const size_t VN = (size_t)b->n_variants * b->n_nodes;
@@ -63,9 +63,10 @@ size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) 
     w.a1 = a.take<float>(ec * H);
     w.e2 = a.take<float>(ec * H);
   } else {
-    w.h16 = a.take<__half>(VN * H);
-    w.cat16 = a.take<__half>(VN * H2);
-    w.z16 = a.take<__half>(VN * H);
+    const size_t VNp = (VN + 127) / 128 * 128;   // row-panel layout: whole panels of 128 rows
+    w.h16 = a.take<__half>(VNp * H);
+    w.cat16 = a.take<__half>(VNp * H2);
+    w.z16 = a.take<__half>(VNp * H);
   }
   return a.off;
 }
@@ -148,7 +149,7 @@ static int f32_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_
       CB2_TRY(launch_sgemm_nt(w.h, H, m->film_wp, w.y, H, VN, H, H, e, st));
     }
     CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
-                              w.cat, H2, nullptr, 0, N, B, V, st));
+                              w.cat, H2, nullptr, 0, 0, N, B, V, st));
     CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
     {
       GemmEpilogue e;  // P = hn [W_hi;W_hj]^T, lattice term + b1 folded into the P_i half
@@ -275,7 +276,7 @@ int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const 
     return f32_edge_layer(L, b, frac_coords, P, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
   }
   if (!L.w_fd_t || !L.w2_t) return fail(CB2_ERR_BAD_ARG, "edge_layer: fp16 operand images missing");
-  return tc_edge_layer(L, b, frac_coords, P, (__half *)agg, ld_agg, 0, (cudaStream_t)stream);
+  return tc_edge_layer(L, b, frac_coords, P, (__half *)agg, ld_agg, 0, 0, (cudaStream_t)stream);
 }
 
 int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, void *workspace,

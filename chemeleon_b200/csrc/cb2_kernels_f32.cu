@@ -225,14 +225,29 @@ __device__ __forceinline__ void store_row_half(__half *__restrict__ p, const flo
   }
 }
 
+// fp16 copy of a normalised row in the row-panel layout [rows/128][kt/8][128][8] the tensor-core
+// GEMMs read their A operand from (lane pairs write one 16-byte core-matrix row).
+__device__ __forceinline__ void store_row_half_panel(__half *__restrict__ base, int64_t row, int kt,
+                                                     const float (&v)[16], int lane) {
+  __half *p = base + (row >> 7) * 128 * kt + (row & 127) * 8;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; q4++) {
+    const int c = (lane + 32 * q4) * 4;
+    uint2 u;
+    u.x = pack_half2_sat(v[q4 * 4 + 0], v[q4 * 4 + 1]);
+    u.y = pack_half2_sat(v[q4 * 4 + 2], v[q4 * 4 + 3]);
+    *reinterpret_cast<uint2 *>(p + (c >> 3) * 1024 + (c & 7)) = u;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_film_apply(const float *__restrict__ y, float *__restrict__ h,
                                                     const float *__restrict__ cond,
                                                     const int32_t *__restrict__ node2graph,
                                                     const float *__restrict__ fg, const float *__restrict__ fb,
                                                     const float *__restrict__ cg, const float *__restrict__ cb,
                                                     float *__restrict__ hn, int64_t ld_hn,
-                                                    __half *__restrict__ hn16, int64_t ld_hn16, int N, int B,
-                                                    int64_t rows) {
+                                                    __half *__restrict__ hn16, int64_t ld_hn16, int hn16_kt,
+                                                    int N, int B, int64_t rows) {
   int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -261,16 +276,19 @@ __global__ void __launch_bounds__(256) k_film_apply(const float *__restrict__ y,
   }
   ln_row(v, cg, cb, lane);
   if (hn != nullptr) store_row(hn + row * ld_hn, v, lane);
-  if (hn16 != nullptr) store_row_half(hn16 + row * ld_hn16, v, lane);
+  if (hn16 != nullptr) {
+    if (hn16_kt > 0) store_row_half_panel(hn16, row, hn16_kt, v, lane);
+    else store_row_half(hn16 + row * ld_hn16, v, lane);
+  }
 }
 
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
-                      int64_t ld_hn16, int N, int B, int V, cudaStream_t st) {
+                      int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st) {
   int64_t rows = (int64_t)V * N;
   if (rows == 0) return CB2_OK;
   k_film_apply<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(y, h, cond, node2graph, fg, fb, cg, cb, hn, ld_hn,
-                                                          hn16, ld_hn16, N, B, rows);
+                                                          hn16, ld_hn16, hn16_kt, N, B, rows);
   CB2_LAUNCH_OK("k_film_apply");
   return CB2_OK;
 }

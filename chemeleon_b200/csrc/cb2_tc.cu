@@ -16,62 +16,77 @@ namespace cb2 {
 using namespace ptx;
 
 // =============================================================================================
-// k_tc_linear: 128 x 256 output tile per CTA, K streamed in chunks of 32 through a 4-stage ring
-// (96 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so that one CTA's
-// epilogue overlaps the other's main loop).
-//   warps 0-3: load the A chunk (fp16 row-major global -> canonical smem), later the epilogue
-//   warp 4   : TMEM alloc, MMA issue (one lane)
+// k_tc_linear: persistent, warp-specialised GEMM  C = epi(A16 W16^T).
+//   One CTA per SM walks over 128 x 256 output tiles (n fastest, so that the CTAs working on one
+//   row panel at the same time share its A chunks through L2).  K is streamed in chunks of 64
+//   through a 3-stage ring (48 KB per stage: 16 KB of A + 32 KB of W), two 256-column TMEM
+//   accumulators let the epilogue of tile t overlap the main loop of tile t+1.
+//     warp 0   : loader - bulk async copies only.  The fp16 activations live in HBM in the
+//                "row-panel" layout [M/128][K/8][128 rows][8 halves], i.e. already in the canonical
+//                K-major shared-memory order, so one chunk of A is ONE contiguous 16 KB copy
+//     warp 1   : TMEM alloc, MMA issue (one lane)
+//     warps 2-17: epilogue (a single warp per scheduler is issue-latency-bound: measured).  TMEM
+//                hands every thread one row; 32 x 32 blocks are transposed through shared memory so
+//                that bias / per-crystal bias / residual loads and the fp32 + fp16 stores are
+//                coalesced (4 rows x 128 B per instruction)
 // =============================================================================================
-constexpr int TL_BM = 128, TL_NB = 256, TL_KC = 32, TL_STAGES = 4;
-constexpr int TL_A_BYTES = TL_BM * TL_KC * 2;   // 8 KB
-constexpr int TL_W_BYTES = TL_NB * TL_KC * 2;   // 16 KB
+constexpr int TL_BM = 128, TL_NB = 256, TL_KC = 64, TL_STAGES = 3;
+constexpr int TL_A_BYTES = TL_BM * TL_KC * 2;   // 16 KB
+constexpr int TL_W_BYTES = TL_NB * TL_KC * 2;   // 32 KB
 constexpr int TL_STAGE_BYTES = TL_A_BYTES + TL_W_BYTES;
-constexpr int TL_SMEM = TL_STAGES * TL_STAGE_BYTES + 1024;
+constexpr int TL_PITCH = 36;                    // floats per staged row (16-byte aligned, +4 pad: conflict-free)
+constexpr int TL_STG_BYTES = 16 * 32 * TL_PITCH * 4;   // one 32 x 32 fp32 block per epilogue warp
+constexpr int TL_SMEM = TL_STAGES * TL_STAGE_BYTES + TL_STG_BYTES + 256;
+constexpr int TL_THREADS = 32 * 18;
 
 struct TcLinearArgs {
-  const __half *A;
-  int64_t lda;
+  const __half *A;    // row-panel layout, a_kt columns per panel; columns [0,K) are consumed
+  int a_kt;
   int64_t M;
   int K;
   const __half *Wt;   // operand image [K/8][Nw][8]
   int Nw;
-  float *C;
+  float *C;           // fp32 row-major output (optional)
   int64_t ldc;
-  __half *C16;
-  int64_t ldc16;
+  __half *C16;        // fp16 row-panel output (optional): c16_kt columns per panel, written at [c16_k0, c16_k0+Nw)
+  int c16_kt, c16_k0;
   const float *bias;
   int silu;
   const float *residual;
   int64_t ldr;
-  const float *gbias;
+  const float *gbias;     // per-crystal additive term, row r uses gbias[gidx[r % gmod]][c] for c < gcols
   const int32_t *gidx;
   int gmod, gcols, gld;
 };
 
-__global__ void __launch_bounds__(160, 2) k_tc_linear(TcLinearArgs g) {
+__global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_base = sbase + TL_STAGES * TL_STAGE_BYTES;
+  const uint32_t bar_base = sbase + TL_STAGES * TL_STAGE_BYTES + TL_STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8 * s; };
-  auto empty_bar = [&](int s) { return bar_base + 64 + 8 * s; };
-  const uint32_t acc_bar = bar_base + 128;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TL_STAGES * TL_STAGE_BYTES + 192);
+  auto empty_bar = [&](int s) { return bar_base + 32 + 8 * s; };
+  auto acc_full = [&](int b) { return bar_base + 64 + 8 * b; };
+  auto acc_empty = [&](int b) { return bar_base + 80 + 8 * b; };
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TL_STAGES * TL_STAGE_BYTES + TL_STG_BYTES + 96);
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const int64_t m0 = (int64_t)blockIdx.x * TL_BM;
-  const int n0 = blockIdx.y * TL_NB;
+  const int n_nt = g.Nw / TL_NB;
+  const int n_tiles = (int)((g.M + TL_BM - 1) / TL_BM) * n_nt;
   const int nk = g.K / TL_KC;
 
   if (tid == 0) {
     for (int s = 0; s < TL_STAGES; s++) {
-      mbar_init(full_bar(s), 129);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 16);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) {
-    tmem_alloc(smem_u32(tmem_slot), TL_NB);
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -79,139 +94,124 @@ __global__ void __launch_bounds__(160, 2) k_tc_linear(TcLinearArgs g) {
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
-    // ---------------- producer ----------------
-    const int r = tid;  // row of the tile
-    const int64_t grow = m0 + r;
-    const bool valid = grow < g.M;
-    const __half *arow = g.A + (valid ? grow : 0) * g.lda;
-    // the A rows are prefetched three K chunks ahead into registers (the loads of one chunk are
-    // only 64 B per thread: without the look-ahead this loop is latency-bound)
-    constexpr int PF = 3;
-    uint4 pre[PF + 1][TL_KC / 8];
-    auto gload = [&](uint4 (&dst)[TL_KC / 8], int kc) {
+  if (warp == 0) {
+    // ---------------- loader ----------------
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int mt = t / n_nt, n0 = (t % n_nt) * TL_NB;
+        const __half *ap = g.A + (int64_t)mt * TL_BM * g.a_kt;
+        for (int kc = 0; kc < nk; kc++, it++) {
+          const int s = it % TL_STAGES;
+          mbar_wait(empty_bar(s), ((it / TL_STAGES) & 1) ^ 1);
+          const uint32_t a_s = sbase + s * TL_STAGE_BYTES, w_s = a_s + TL_A_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), TL_STAGE_BYTES);
+          bulk_g2s(a_s, ap + (int64_t)kc * (TL_KC / 8) * (TL_BM * 8), TL_A_BYTES, full_bar(s));
 #pragma unroll
-      for (int k8 = 0; k8 < TL_KC / 8; k8++)
-        dst[k8] = valid ? *reinterpret_cast<const uint4 *>(arow + kc * TL_KC + k8 * 8) : make_uint4(0, 0, 0, 0);
-    };
-#pragma unroll
-    for (int u = 0; u < PF; u++)
-      if (u < nk) gload(pre[u], u);
-    for (int kc0 = 0; kc0 < nk; kc0 += PF + 1) {
-#pragma unroll
-      for (int u = 0; u <= PF; u++) {
-        const int kc = kc0 + u;
-        if (kc >= nk) break;
-        if (kc + PF < nk) gload(pre[(u + PF) % (PF + 1)], kc + PF);
-        const int s = kc % TL_STAGES;
-        mbar_wait(empty_bar(s), ((kc / TL_STAGES) & 1) ^ 1);
-        const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
-        const uint32_t w_s = a_s + TL_A_BYTES;
-        if (tid == 0) {
-          mbar_arrive_expect_tx(full_bar(s), TL_W_BYTES);
-#pragma unroll
-          for (int k8 = 0; k8 < TL_KC / 8; k8++) {
-            const __half *src = g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8;
-            bulk_g2s(w_s + k8 * (TL_NB * 16), src, TL_NB * 16, full_bar(s));
-          }
-        }
-#pragma unroll
-        for (int k8 = 0; k8 < TL_KC / 8; k8++)
-          *reinterpret_cast<uint4 *>(smem + s * TL_STAGE_BYTES + k8 * (TL_BM * 16) + r * 16) = pre[u][k8];
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar(s));
-      }
-    }
-    // ---------------- epilogue ----------------
-    mbar_wait(acc_bar, 0);
-    tc_fence_after_sync();
-    const float *gb = nullptr;
-    if (g.gbias != nullptr && valid) gb = g.gbias + (int64_t)g.gidx[grow % g.gmod] * g.gld;
-#pragma unroll 1
-    for (int c0 = 0; c0 < TL_NB; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int c = n0 + c0 + j;
-        float x = __uint_as_float(acc[j]);
-        if (g.bias != nullptr) x += g.bias[c];
-        if (gb != nullptr && c < g.gcols) x += gb[c];
-        if (g.silu) x = silu_fast(x);
-        v[j] = x;
-      }
-      if (g.residual != nullptr) {
-        const float4 *rr = reinterpret_cast<const float4 *>(g.residual + grow * g.ldr + n0 + c0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          float4 t = rr[j];
-          v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          for (int k8 = 0; k8 < TL_KC / 8; k8++)
+            bulk_g2s(w_s + k8 * (TL_NB * 16), g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8, TL_NB * 16,
+                     full_bar(s));
         }
       }
-      if (g.C != nullptr) {
-        float4 *cc = reinterpret_cast<float4 *>(g.C + grow * g.ldc + n0 + c0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) cc[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      if (g.C16 != nullptr) {
-        uint4 *cc = reinterpret_cast<uint4 *>(g.C16 + grow * g.ldc16 + n0 + c0);
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          cc[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
-      }
     }
-    tc_fence_before_sync();
-  } else {
+    __syncwarp();
+  } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_f16_f32(TL_BM, TL_NB);
-      for (int kc = 0; kc < nk; kc++) {
-        const int s = kc % TL_STAGES;
-        mbar_wait(full_bar(s), (kc / TL_STAGES) & 1);
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+        const int buf = tl & 1;
+        mbar_wait(acc_empty(buf), ((tl >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t a_s = sbase + s * TL_STAGE_BYTES;
-        const uint32_t w_s = a_s + TL_A_BYTES;
+        for (int kc = 0; kc < nk; kc++, it++) {
+          const int s = it % TL_STAGES;
+          mbar_wait(full_bar(s), (it / TL_STAGES) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_s = sbase + s * TL_STAGE_BYTES, w_s = a_s + TL_A_BYTES;
 #pragma unroll
-        for (int j = 0; j < TL_KC / 16; j++) {
-          const uint64_t ad = smem_desc_kmajor(a_s + 2 * j * (TL_BM * 16), TL_BM * 16, 128);
-          const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * (TL_NB * 16), TL_NB * 16, 128);
-          umma_f16(tmem, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < TL_KC / 16; j++) {
+            const uint64_t ad = smem_desc_kmajor(a_s + 2 * j * (TL_BM * 16), TL_BM * 16, 128);
+            const uint64_t bd = smem_desc_kmajor(w_s + 2 * j * (TL_NB * 16), TL_NB * 16, 128);
+            umma_f16(tmem + buf * TL_NB, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(acc_full(buf));
       }
-      umma_commit(acc_bar);
     }
     __syncwarp();
+  } else {
+    // ---------------- epilogue (16 warps) ----------------
+    // A warp may only read the TMEM lane quarter warp % 4; the four warps of a quarter split the
+    // 256 columns.  Each warp pulls its 32 x 64 block into registers, hands the accumulator back
+    // to the MMA warp at once, and then writes the block out through its staging rows.
+    const int q = warp & 3, cgrp = (warp - 2) >> 2;
+    float *stg = reinterpret_cast<float *>(smem + TL_STAGES * TL_STAGE_BYTES) + (warp - 2) * (32 * TL_PITCH);
+    const int orow = lane >> 3, ocol = (lane & 7) * 4;             // output pass: 4 rows x 128 B per instruction
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+      const int buf = tl & 1;
+      const int mt = t / n_nt, n0 = (t % n_nt) * TL_NB + cgrp * 64;
+      const int64_t r0 = (int64_t)mt * TL_BM + q * 32;             // first row of this warp
+      const int nvalid = (int)(g.M - r0 < 32 ? g.M - r0 : 32);
+      int gi = 0;
+      if (g.gbias != nullptr && lane < nvalid) gi = g.gidx[(r0 + lane) % g.gmod];
+      mbar_wait(acc_full(buf), (tl >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * TL_NB + cgrp * 64;
+      uint32_t acc[2][32];
+      tmem_ld32(taddr, acc[0]);
+      tmem_ld32(taddr + 32, acc[1]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      const int64_t crow = (r0 + orow) * g.ldc, rrow = (r0 + orow) * g.ldr;
+      __half *c16p = g.C16 ? g.C16 + (int64_t)mt * TL_BM * g.c16_kt + (q * 32 + orow) * 8 : nullptr;
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        __syncwarp();                                              // previous output pass has drained the staging rows
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<uint4 *>(stg + lane * TL_PITCH + 4 * j) =
+              make_uint4(acc[hb][4 * j], acc[hb][4 * j + 1], acc[hb][4 * j + 2], acc[hb][4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + hb * 32 + ocol;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr) b4 = *reinterpret_cast<const float4 *>(g.bias + col);
+        const bool use_gb = g.gbias != nullptr && col < g.gcols;
+        const int c16 = g.c16_k0 + col;
+        __half *c16c = c16p ? c16p + (int64_t)(c16 >> 3) * (TL_BM * 8) + (c16 & 7) : nullptr;
+#pragma unroll
+        for (int itr = 0; itr < 8; itr++) {
+          const int rr = itr * 4 + orow;
+          int gsrc = 0;
+          if (g.gbias != nullptr) gsrc = __shfl_sync(0xffffffffu, gi, rr);
+          if (rr < nvalid) {
+            float4 x = *reinterpret_cast<const float4 *>(stg + rr * TL_PITCH + ocol);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (use_gb) {
+              const float4 t4 = *reinterpret_cast<const float4 *>(g.gbias + (int64_t)gsrc * g.gld + col);
+              x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+            }
+            if (g.silu) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
+            if (g.residual != nullptr) {
+              const float4 t4 = *reinterpret_cast<const float4 *>(g.residual + rrow + (int64_t)itr * 4 * g.ldr + col);
+              x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+            }
+            if (g.C != nullptr) *reinterpret_cast<float4 *>(g.C + crow + (int64_t)itr * 4 * g.ldc + col) = x;
+            if (c16c != nullptr)
+              *reinterpret_cast<uint2 *>(c16c + itr * 32) = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
+          }
+        }
+      }
+    }
   }
+  tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TL_NB);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
-
-int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
-  if (a.M == 0) return CB2_OK;
-  if (a.K % TL_KC != 0 || a.Nw % TL_NB != 0 || (a.lda % 8) != 0)
-    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%32, N%256, lda%8 must be 0");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)((a.M + TL_BM - 1) / TL_BM), (unsigned)(a.Nw / TL_NB));
-  k_tc_linear<<<grid, 160, TL_SMEM, st>>>(a);
-  CB2_LAUNCH_OK("k_tc_linear");
-  return CB2_OK;
-}
-
-// launchers from cb2_kernels_f32.cu reused by the tensor-core path
-int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
-                      const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
-                      int64_t ld_hn16, int N, int B, int V, cudaStream_t st);
-int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
-int launch_to_half(const float *x, __half *y, int64_t n, cudaStream_t st);
 
 static int g_num_sms = 0;
 
@@ -225,61 +225,134 @@ static int num_sms(int *out) {
   return CB2_OK;
 }
 
+int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
+  if (a.M == 0) return CB2_OK;
+  if (a.K % TL_KC != 0 || a.K <= 0 || a.Nw % TL_NB != 0 || a.a_kt % 8 != 0 || a.K > a.a_kt)
+    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, a_kt%8 must be 0 and K <= a_kt");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
+    attr_set = true;
+  }
+  int sms = 0;
+  CB2_TRY(num_sms(&sms));
+  const int64_t n_tiles = ((a.M + TL_BM - 1) / TL_BM) * (a.Nw / TL_NB);
+  k_tc_linear<<<(unsigned)(n_tiles < sms ? n_tiles : sms), TL_THREADS, TL_SMEM, st>>>(a);
+  CB2_LAUNCH_OK("k_tc_linear");
+  return CB2_OK;
+}
+
+// Row-major -> row-panel layout of an fp16 / fp32 activation matrix (rows past M are zero-filled).
+// A warp instruction covers 4 rows x 8 column groups: 256 B reads, 64 B writes per segment.
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_panels(const T *__restrict__ x, int64_t ldx, __half *__restrict__ y, int64_t M,
+                                                   int K, int kt, int k0) {
+  const int k8n = K / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t grp = idx / 32;                 // one warp = 4 rows x 8 column groups
+  const int lane = (int)(idx % 32);
+  const int k8blocks = (k8n + 7) / 8;
+  const int64_t r = (grp / k8blocks) * 4 + lane / 8;
+  const int k8 = (int)(grp % k8blocks) * 8 + lane % 8;
+  const int64_t Mp = (M + 127) / 128 * 128;
+  if (r >= Mp || k8 >= k8n) return;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (r < M) {
+    if constexpr (sizeof(T) == 2) {
+      o = *reinterpret_cast<const uint4 *>(x + r * ldx + k8 * 8);
+    } else {
+      const float4 a = *reinterpret_cast<const float4 *>(x + r * ldx + k8 * 8);
+      const float4 b = *reinterpret_cast<const float4 *>(x + r * ldx + k8 * 8 + 4);
+      o = make_uint4(pack_half2(a.x, a.y), pack_half2(a.z, a.w), pack_half2(b.x, b.y), pack_half2(b.z, b.w));
+    }
+  }
+  *reinterpret_cast<uint4 *>(y + (r / 128) * 128 * kt + (int64_t)((k0 >> 3) + k8) * 1024 + (r % 128) * 8) = o;
+}
+
+template <typename T>
+static int launch_to_panels(const T *x, int64_t ldx, __half *y, int64_t M, int K, int kt, int k0, cudaStream_t st) {
+  if (M == 0) return CB2_OK;
+  const int64_t Mp = (M + 127) / 128 * 128;
+  const int64_t warps = (Mp / 4) * ((K / 8 + 7) / 8);
+  k_to_panels<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, ldx, y, M, K, kt, k0);
+  CB2_LAUNCH_OK("k_to_panels");
+  return CB2_OK;
+}
+
+// launchers from cb2_kernels_f32.cu reused by the tensor-core path
+int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
+                      const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
+                      int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
+int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
+
+// C-ABI unit entry: row-major fp16 A; the row-panel copy the kernel reads is made here.
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
                      int64_t ldc, int64_t M, int K, int silu, cudaStream_t st) {
-  TcLinearArgs a{};
-  a.A = (const __half *)A16; a.lda = lda; a.M = M; a.K = K; a.Wt = (const __half *)Wt; a.Nw = Nw;
-  a.C = C; a.ldc = ldc; a.bias = bias; a.silu = silu;
-  return launch_tc_linear(a, st);
+  if (M == 0) return CB2_OK;
+  if (K % TL_KC != 0 || lda % 8 != 0) return fail(CB2_ERR_BAD_ARG, "linear_tc: K%64 and lda%8 must be 0");
+  __half *panels = nullptr;
+  const int64_t Mp = (M + 127) / 128 * 128;
+  CB2_CUDA_OK(cudaMallocAsync((void **)&panels, (size_t)Mp * K * sizeof(__half), st));
+  int rc = launch_to_panels<__half>((const __half *)A16, lda, panels, M, K, K, 0, st);
+  if (rc == CB2_OK) {
+    TcLinearArgs a{};
+    a.A = panels; a.a_kt = K; a.M = M; a.K = K; a.Wt = (const __half *)Wt; a.Nw = Nw;
+    a.C = C; a.ldc = ldc; a.bias = bias; a.silu = silu;
+    rc = launch_tc_linear(a, st);
+  }
+  CB2_CUDA_OK(cudaFreeAsync(panels, st));
+  return rc;
 }
 
 int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
-                  int64_t ld_agg, int agg_col, cudaStream_t st) {
+                  int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st) {
   int sms = 0;
   CB2_TRY(num_sms(&sms));
   TcEdgeArgs e{};
   e.P = P; e.x = x; e.row_i = b->tile_row_i; e.row_j = b->tile_row_j; e.seg_n = b->tile_seg_n;
   e.w_fd_t = (const __half *)L.w_fd_t; e.w2_t = (const __half *)L.w2_t; e.b2 = L.b2;
-  e.agg16 = agg16; e.ld_agg = ld_agg; e.agg_col = agg_col; e.N = b->n_nodes; e.V = b->n_variants;
+  e.agg16 = agg16; e.ld_agg = ld_agg; e.agg_col = agg_col; e.agg_kt = agg_kt; e.N = b->n_nodes; e.V = b->n_variants;
   e.n_tiles = b->n_tiles;
   return launch_tc_edge(e, sms, st);
 }
 
+// One CSPNet trunk pass on the tensor cores.  fp32 row-major: h (residual stream), y, P;
+// fp16 row-panel: h16, cat16 = [LN(h) | agg], z16.
 int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                       cudaStream_t st) {
   const int N = b->n_nodes, B = b->n_graphs, V = b->n_variants;
   const int64_t VN = (int64_t)V * N;
   if (!m->film_wp_t) return fail(CB2_ERR_BAD_ARG, "tensor-core path needs the fp16 operand images (pack with tensor_core=True)");
-  CB2_TRY(launch_to_half(w.h, w.h16, VN * H, st));
+  if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
   for (int li = 0; li < m->n_layers; li++) {
     const cb2_layer_weights &L = m->layers[li];
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
     if (io->film_cond != nullptr) {
       TcLinearArgs a{};
-      a.A = w.h16; a.lda = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
+      a.A = w.h16; a.a_kt = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
       a.C = w.y; a.ldc = H; a.bias = m->film_bp;
       CB2_TRY(launch_tc_linear(a, st));
     }
     CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
-                              nullptr, 0, w.cat16, H2, N, B, V, st));
+                              nullptr, 0, w.cat16, 0, H2, N, B, V, st));
     CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
     {
       TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T  (+ lattice term + b1 on the P_i half)
-      a.A = w.cat16; a.lda = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
+      a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
       a.C = w.P; a.ldc = H2;
       a.gbias = w.cg; a.gidx = b->node2graph; a.gmod = N; a.gcols = H; a.gld = H;
       CB2_TRY(launch_tc_linear(a, st));
     }
-    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, w.P, w.cat16, H2, H, st));
+    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, w.P, w.cat16, 0, H, H2, st));
     {
       TcLinearArgs a{};   // z = SiLU([hn|agg] Wn1^T + bn1)
-      a.A = w.cat16; a.lda = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;
-      a.C16 = w.z16; a.ldc16 = H; a.bias = L.bn1; a.silu = 1;
+      a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;
+      a.C16 = w.z16; a.c16_kt = H; a.bias = L.bn1; a.silu = 1;
       CB2_TRY(launch_tc_linear(a, st));
       TcLinearArgs a2{};  // h = h + SiLU(z Wn2^T + bn2)
-      a2.A = w.z16; a2.lda = H; a2.M = VN; a2.K = H; a2.Wt = (const __half *)L.wn2_t; a2.Nw = H;
-      a2.C = w.h; a2.ldc = H; a2.C16 = w.h16; a2.ldc16 = H; a2.bias = L.bn2; a2.silu = 1;
+      a2.A = w.z16; a2.a_kt = H; a2.M = VN; a2.K = H; a2.Wt = (const __half *)L.wn2_t; a2.Nw = H;
+      a2.C = w.h; a2.ldc = H; a2.C16 = w.h16; a2.c16_kt = H; a2.bias = L.bn2; a2.silu = 1;
       a2.residual = w.h; a2.ldr = H;
       CB2_TRY(launch_tc_linear(a2, st));
     }

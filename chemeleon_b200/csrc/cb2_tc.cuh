@@ -28,9 +28,10 @@ struct TcEdgeArgs {
   const __half *w_fd_t;    // [96][512][8]      K-major image of W_fd (kernel column order)
   const __half *w2_t;      // [4][64][128][8]   K-major image of W2, one block of 128 output channels each
   const float *b2;
-  __half *agg16;           // [V*N, ld_agg], written at column offset agg_col
-  int64_t ld_agg;
+  __half *agg16;           // [V*N, ld_agg] row-major, or row-panel layout with agg_kt columns per
+  int64_t ld_agg;          // panel when agg_kt > 0; written at column offset agg_col
   int agg_col;
+  int agg_kt;
   int N, V, n_tiles;
 };
 

@@ -61,23 +61,32 @@ __device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
 // ---- E2 body: mean over the n edges of each segment of SiLU(U + b2) for one TMEM unit ----
 // Segment boundaries are compile-time for N > 0 (no branches in the running sum); N == 0 is
 // the generic runtime-n version used for segment lengths without a specialisation.
-__device__ __forceinline__ void e2_store(const uint32_t *t_oi, int seg0, __half *out, int64_t ld_agg, float mean) {
+// Output row r of channel c lives at out[(r / 128) * ld_agg.hi + (r % 128) * ld_agg.lo]: row-major
+// (hi = 128 ld, lo = ld) or the row-panel layout of the GEMM A operands (hi = 128 kt, lo = 8).
+struct AggStride { int64_t hi; int lo; };
+__device__ __forceinline__ void e2_store(const uint32_t *t_oi, int seg0, __half *out, AggStride ld_agg, float mean) {
   const uint32_t o = t_oi[seg0];
-  if (o != TE_PAD) out[(int64_t)(o >> 10) * ld_agg] = __float2half_rn(fminf(fmaxf(mean, -65504.f), 65504.f));
+  if (o != TE_PAD) {
+    const uint32_t r = o >> 10;
+    out[(int64_t)(r >> 7) * ld_agg.hi + (int)(r & 127) * ld_agg.lo] = __float2half_rn(fminf(fmaxf(mean, -65504.f), 65504.f));
+  }
 }
 
 template <int N>
 __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
-                                     int64_t ld_agg) {
+                                     AggStride ld_agg) {
   const int n = N > 0 ? N : n_rt;
   const float inv_n = 1.0f / (float)n;
   float sum = 0.f;
   int cnt = 0, seg0 = 0;
+  uint32_t accA[32], accB[32];
+  tmem_ld32(taddr, accA);
 #pragma unroll
   for (int cb = 0; cb < 4; cb++) {
-    uint32_t acc[32];
-    tmem_ld32(taddr + cb * 32, acc);
     tmem_ld_wait();
+    uint32_t (&acc)[32] = (cb & 1) ? accB : accA;
+    uint32_t (&nxt)[32] = (cb & 1) ? accA : accB;
+    if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);   // next chunk's TMEM read overlaps this chunk's math
     float t[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
@@ -100,7 +109,7 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
 }
 
 __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
-                                            int64_t ld_agg) {
+                                            AggStride ld_agg) {
   switch (n) {
 #define CB2_E2_CASE(N) case N: e2_unit<N>(n, taddr, bias, t_oi, out, ld_agg); break;
     CB2_E2_CASE(1) CB2_E2_CASE(2) CB2_E2_CASE(3) CB2_E2_CASE(4) CB2_E2_CASE(5) CB2_E2_CASE(6) CB2_E2_CASE(7)
@@ -349,7 +358,10 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     const int c = u4 * 128 + q * 32 + lane;      // output channel owned in the epilogues
     const float *Pc = g.P + c;
     const float bias = __ldg(g.b2 + c);
-    __half *out = g.agg16 + g.agg_col + c;
+    const int oc = g.agg_col + c;
+    __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
+    const AggStride agg_ld = g.agg_kt > 0 ? AggStride{(int64_t)128 * g.agg_kt, 8}
+                                          : AggStride{(int64_t)128 * g.ld_agg, (int)g.ld_agg};
     uint8_t *a1_dst = smem + (size_t)(c / 8) * 2048 + (c % 8) * 16;
 
     // The (i, j) node ids of this thread's edge row are fetched one item ahead (fetch_rows); the
@@ -464,19 +476,26 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       mbar_wait(acc1_full, it & 1);
       tc_fence_after_sync();
       if (tid == 0) TE_STAMP(9);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; cb++) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + cb * 32, acc);
-        tmem_ld_wait();
+      {
+        // TMEM reads (64 B/clk/SM) and the MUFU-bound SiLU are overlapped: the load of chunk cb+1 is
+        // in flight while chunk cb is processed
+        uint32_t accA[32], accB[32];
+        tmem_ld32(taddr, accA);
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-          uint32_t w[4];
+        for (int cb = 0; cb < 4; cb++) {
+          tmem_ld_wait();
+          uint32_t (&cur)[32] = (cb & 1) ? accB : accA;
+          uint32_t (&nxt)[32] = (cb & 1) ? accA : accB;
+          if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);
 #pragma unroll
-          for (int e = 0; e < 4; e++)
-            w[e] = pack_half2(silu_fast(__uint_as_float(acc[8 * p + 2 * e])),
-                              silu_fast(__uint_as_float(acc[8 * p + 2 * e + 1])));
-          *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int p = 0; p < 4; p++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              w[e] = pack_half2(silu_fast(__uint_as_float(cur[8 * p + 2 * e])),
+                                silu_fast(__uint_as_float(cur[8 * p + 2 * e + 1])));
+            *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
       {  // pre-load the unit with b2: every GEMM2 MMA accumulates, so the issuers need no ordering
@@ -499,7 +518,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         mbar_wait(acc2_full(u4), it & 1);
         tc_fence_after_sync();
         if (lane == 0 && q == 0) TE_STAMP(11 + 4 * u4);
-        e2_dispatch(n, taddr, bias, t_oi, out, g.ld_agg);
+        e2_dispatch(n, taddr, bias, t_oi, out, agg_ld);
         if (lane == 0 && q == 0) TE_STAMP(12 + 4 * u4);
         tc_fence_before_sync();
         if (has_next) init_unit(buf ^ 1, g.seg_n[next % g.n_tiles]);

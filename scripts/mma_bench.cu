@@ -261,6 +261,55 @@ void run_poll(int iters, unsigned long long *d, int smem_bytes) {
   }
 }
 
+// transposed orientation with narrow N (edges): A = weights block (M=128), B = NE edges
+template <int NE>
+__global__ void __launch_bounds__(128, 1) k_mma_narrow(int iters, unsigned long long *cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const uint32_t sbase = smem_u32(smem);
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tslot), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tslot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = idesc_f16_f32(128, NE);
+    const uint64_t d2k = smem_desc_kmajor(sbase, 2048, 128);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+      // one 32 KB stage of W2-like weights: [16 k8][128 ch][16 B] -> 8 k-steps for one 128-channel unit
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint64_t ad = d2k + (uint64_t)((65536 + ((it % 3) * 32768) + 2 * j * 2048) >> 4);
+        const uint64_t bd = d2k + (uint64_t)((((it & 3) * 16 + 2 * j) * 2048) >> 4);
+        umma_f16(tmem + (it & 3) * 128, ad, bd, idesc, it > 3 || j > 0);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) cycles[0] = (unsigned long long)(t1 - t0);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int NE>
+void run_narrow(int iters, unsigned long long *d, int smem_bytes) {
+  cudaFuncSetAttribute(k_mma_narrow<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  for (int rep = 0; rep < 2; rep++) {
+    k_mma_narrow<NE><<<148, 128, smem_bytes>>>(iters, d);
+    cudaError_t err = cudaDeviceSynchronize();
+    unsigned long long cyc = 0;
+    cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+    if (rep) printf("NARROW M128 N%d: err=%d cycles per 8 MMAs=%.1f  (ideal %d)\n", NE, (int)err, (double)cyc / iters, NE * 4);
+  }
+}
+
 template <int NW, int NC>
 void run_sync(int iters, unsigned long long *d, int smem_bytes) {
   cudaFuncSetAttribute(k_mma_sync<NW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -301,6 +350,9 @@ int main() {
              flops / (ms * 1e-3) / 1e12, (double)cyc / iters);
     }
   }
+  run_narrow<128>(iters, d, smem_bytes);
+  run_narrow<64>(iters, d, smem_bytes);
+  run_narrow<32>(iters, d, smem_bytes);
   run_poll<0>(iters, d, smem_bytes);
   run_poll<1>(iters, d, smem_bytes);
   run_poll<2>(iters, d, smem_bytes);
