@@ -89,7 +89,12 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
     if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);   // next chunk's TMEM read overlaps this chunk's math
     float t[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
+    for (int j = 0; j < 32; j += 2) {       // b2 is already in the accumulator
+      const uint32_t y = silu2_half(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
+      const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&y));
+      t[j] = f.x;
+      t[j + 1] = f.y;
+    }
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       sum += t[j];
@@ -123,29 +128,43 @@ __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, c
   }
 }
 
-// ---- accumulator init: U[c][e] = P_i[i(e)][c] + P_j[j(e)][c] for one lane quarter of a unit ----
-// N > 0: the tile's segment structure is compile-time, so each thread loads P_i once per
-// segment and the N rows of P_j once per crystal (they repeat for every segment of the same
-// crystal) instead of two values per edge.  N == 0: generic version, two gathers per edge.
+// ---- E1 body: a1[c][e] = SiLU(U[c][e] + P_i[i(e)][c] + P_j[j(e)][c]) for one lane quarter of a unit ----
+// The hoisted node terms are gathered thread = channel (128 B per warp and node) BEFORE the wait
+// on the GEMM1 accumulator, so their latency is off the critical path.  N > 0: the tile's segment
+// structure is compile-time, each thread loads P_i once per segment and the N rows of P_j once
+// per crystal (they repeat for every segment of the same crystal).  N == 0: generic version, two
+// gathers per edge.
 template <int N>
-__device__ __noinline__ void init_unit_t(uint32_t taddr, const float *Pc, const uint32_t *t_oi,
-                                         const uint32_t *t_oj) {
+__device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint32_t *t_oi, const uint32_t *t_oj,
+                                     uint8_t *a1_dst, uint32_t acc1_full, uint32_t parity) {
   if constexpr (N == 0) {
     const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
     const uint4 *tj = reinterpret_cast<const uint4 *>(t_oj);
+    mbar_wait(acc1_full, parity);
+    tc_fence_after_sync();
 #pragma unroll 1
     for (int cb = 0; cb < 4; cb++) {
-      uint32_t val[32];
+      uint32_t acc[32];
+      tmem_ld32(taddr + cb * 32, acc);
+      float pv[32];
 #pragma unroll
       for (int j4 = 0; j4 < 8; j4++) {
         const uint4 oi = ti[cb * 8 + j4], oj = tj[cb * 8 + j4];
         const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
         const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          val[j4 * 4 + k] = __float_as_uint(Pc[ois[k] == TE_PAD ? 0u : ois[k]] + Pc[ojs[k]]);
+        for (int k = 0; k < 4; k++) pv[j4 * 4 + k] = Pc[ois[k] == TE_PAD ? 0u : ois[k]] + Pc[ojs[k]];
       }
-      tmem_st32(taddr + cb * 32, val);
+      tmem_ld_wait();
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          w[e] = silu2_half(__uint_as_float(acc[8 * p + 2 * e]) + pv[8 * p + 2 * e],
+                            __uint_as_float(acc[8 * p + 2 * e + 1]) + pv[8 * p + 2 * e + 1]);
+        *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   } else {
     constexpr int S = 128 / N;
@@ -159,12 +178,23 @@ __device__ __noinline__ void init_unit_t(uint32_t taddr, const float *Pc, const 
     uint32_t cur = t_oj[0];
 #pragma unroll
     for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
+    mbar_wait(acc1_full, parity);
+    tc_fence_after_sync();
+    // 16-column TMEM loads, double-buffered: the load of block hb+1 is in flight while block hb
+    // goes through the SiLU (register budget: 2 x 16 accumulators + P_i / P_j values)
+    uint32_t accA[16], accB[16];
+    tmem_ld16(taddr, accA);
 #pragma unroll
-    for (int cb = 0; cb < 4; cb++) {
-      uint32_t val[32];
+    for (int hb = 0; hb < 8; hb++) {
+      tmem_ld_wait();
+      uint32_t (&acc)[16] = (hb & 1) ? accB : accA;
+      uint32_t (&nxt)[16] = (hb & 1) ? accA : accB;
+      if (hb < 7) tmem_ld16(taddr + (hb + 1) * 16, nxt);
+      float x[16];
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int e = cb * 32 + j;
+      for (int j = 0; j < 16; j++) {
+        const int e = hb * 16 + j;
+        x[j] = __uint_as_float(acc[j]);
         if (e < S * N) {
           if (e % N == 0 && e > 0) {            // segment start: same crystal as before?
             const uint32_t oj0 = t_oj[e];
@@ -174,29 +204,34 @@ __device__ __noinline__ void init_unit_t(uint32_t taddr, const float *Pc, const 
               for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
             }
           }
-          val[j] = __float_as_uint(piv[e / N] + pj[e % N]);
-        } else {
-          val[j] = 0u;
+          x[j] += piv[e / N] + pj[e % N];
         }
       }
-      tmem_st32(taddr + cb * 32, val);
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) w[e] = silu2_half(x[8 * p + 2 * e], x[8 * p + 2 * e + 1]);
+        *reinterpret_cast<uint4 *>(a1_dst + (hb * 2 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   }
 }
 
-__device__ __forceinline__ void init_dispatch(int n, uint32_t taddr, const float *Pc, const uint32_t *t_oi,
-                                              const uint32_t *t_oj) {
+__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const float *Pc, const uint32_t *t_oi,
+                                            const uint32_t *t_oj, uint8_t *a1_dst, uint32_t acc1_full,
+                                            uint32_t parity) {
   switch (n) {
-#define CB2_INIT_CASE(N) case N: init_unit_t<N>(taddr, Pc, t_oi, t_oj); break;
-    CB2_INIT_CASE(4) CB2_INIT_CASE(5) CB2_INIT_CASE(6) CB2_INIT_CASE(7)
-    CB2_INIT_CASE(8) CB2_INIT_CASE(9) CB2_INIT_CASE(10) CB2_INIT_CASE(11) CB2_INIT_CASE(12) CB2_INIT_CASE(13)
-    CB2_INIT_CASE(14) CB2_INIT_CASE(15) CB2_INIT_CASE(16) CB2_INIT_CASE(17) CB2_INIT_CASE(18) CB2_INIT_CASE(19)
-    CB2_INIT_CASE(20) CB2_INIT_CASE(21) CB2_INIT_CASE(22) CB2_INIT_CASE(23) CB2_INIT_CASE(24) CB2_INIT_CASE(25)
-    CB2_INIT_CASE(26) CB2_INIT_CASE(27) CB2_INIT_CASE(28) CB2_INIT_CASE(29) CB2_INIT_CASE(30) CB2_INIT_CASE(31)
-    CB2_INIT_CASE(32) CB2_INIT_CASE(33) CB2_INIT_CASE(34) CB2_INIT_CASE(35) CB2_INIT_CASE(36) CB2_INIT_CASE(37)
-    CB2_INIT_CASE(38) CB2_INIT_CASE(39) CB2_INIT_CASE(40)
-#undef CB2_INIT_CASE
-    default: init_unit_t<0>(taddr, Pc, t_oi, t_oj); break;
+#define CB2_E1_CASE(N) case N: e1_unit<N>(taddr, Pc, t_oi, t_oj, a1_dst, acc1_full, parity); break;
+    CB2_E1_CASE(4) CB2_E1_CASE(5) CB2_E1_CASE(6) CB2_E1_CASE(7)
+    CB2_E1_CASE(8) CB2_E1_CASE(9) CB2_E1_CASE(10) CB2_E1_CASE(11) CB2_E1_CASE(12) CB2_E1_CASE(13)
+    CB2_E1_CASE(14) CB2_E1_CASE(15) CB2_E1_CASE(16) CB2_E1_CASE(17) CB2_E1_CASE(18) CB2_E1_CASE(19)
+    CB2_E1_CASE(20) CB2_E1_CASE(21) CB2_E1_CASE(22) CB2_E1_CASE(23) CB2_E1_CASE(24) CB2_E1_CASE(25)
+    CB2_E1_CASE(26) CB2_E1_CASE(27) CB2_E1_CASE(28) CB2_E1_CASE(29) CB2_E1_CASE(30) CB2_E1_CASE(31)
+    CB2_E1_CASE(32) CB2_E1_CASE(33) CB2_E1_CASE(34) CB2_E1_CASE(35) CB2_E1_CASE(36) CB2_E1_CASE(37)
+    CB2_E1_CASE(38) CB2_E1_CASE(39) CB2_E1_CASE(40)
+#undef CB2_E1_CASE
+    default: e1_unit<0>(taddr, Pc, t_oi, t_oj, a1_dst, acc1_full, parity); break;
   }
 }
 
@@ -225,7 +260,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
   auto acc2_full = [&](int u) { return bars + 224 + 8 * u; };
   auto acc_init = [&](int u) { return bars + 256 + 8 * u; };
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 288);
-  const uint32_t ready_addr = bars + 296;   // number of MMA-thread wait points the scout has cleared
+
   // weight stage s: 0..2 = ring R1, 3..4 = extra stages inside the a1 region (GEMM1 only)
   auto w_addr = [&](int s) {
     return s < TE_WSTAGES ? sbase + TE_W_OFF + s * TE_W_BYTES : sbase + TE_WEXTRA_OFF + (s - TE_WSTAGES) * TE_W_BYTES;
@@ -391,7 +426,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         tab[buf * 256 + 128 + r] = oj;
       }
     };
-    // pull the tile's rows of P towards L2 long before init_unit gathers them
+    // pull the tile's rows of P towards L2 long before E1 gathers them
     auto prefetch_rows = [&](int buf) {
       if (warp < 8) {
         const int e = (warp * 32 + lane) >> 1;
@@ -403,9 +438,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         }
       }
     };
-    // U[c][e] = P_i[i(e)][c] + P_j[j(e)][c] for this warp's lane quarter of its unit
-    auto init_unit = [&](int buf, int n_tile) {
-      init_dispatch(n_tile, taddr, Pc, tab + buf * 256, tab + buf * 256 + 128);
+    // GEMM1 accumulates onto zeros (the hoisted terms P_i + P_j are added in E1)
+    auto clear_unit = [&]() {
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) z[j] = 0u;
+#pragma unroll
+      for (int cb = 0; cb < 4; cb++) tmem_st32(taddr + cb * 32, z);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(acc_init(u4));
@@ -417,7 +456,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     fetch_rows(blockIdx.x);
     publish_rows(blockIdx.x, 0, dlt);
     TE_WORKER_BARRIER();
-    init_unit(0, g.seg_n[blockIdx.x % g.n_tiles]);
+    clear_unit();
     if ((int)(blockIdx.x + gridDim.x) < n_items) fetch_rows(blockIdx.x + gridDim.x);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
       const int buf = it & 1;
@@ -471,33 +510,10 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       // every group has finished the previous item (its tables are dead): publish the next item's
       TE_WORKER_BARRIER();
       if (has_next) publish_rows(next, buf ^ 1, dlt_next);
-      // ---- E1: a1 = SiLU(U), thread = channel, MN-major fp16 operand of GEMM2 ----
+      // ---- E1: a1 = SiLU(U + P_i + P_j), thread = channel, MN-major fp16 operand of GEMM2 ----
       if (tid == 0) TE_STAMP(8);
-      mbar_wait(acc1_full, it & 1);
-      tc_fence_after_sync();
+      e1_dispatch(n, taddr, Pc, t_oi, t_oi + 128, a1_dst, acc1_full, it & 1);
       if (tid == 0) TE_STAMP(9);
-      {
-        // TMEM reads (64 B/clk/SM) and the MUFU-bound SiLU are overlapped: the load of chunk cb+1 is
-        // in flight while chunk cb is processed
-        uint32_t accA[32], accB[32];
-        tmem_ld32(taddr, accA);
-#pragma unroll
-        for (int cb = 0; cb < 4; cb++) {
-          tmem_ld_wait();
-          uint32_t (&cur)[32] = (cb & 1) ? accB : accA;
-          uint32_t (&nxt)[32] = (cb & 1) ? accA : accB;
-          if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);
-#pragma unroll
-          for (int p = 0; p < 4; p++) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              w[e] = pack_half2(silu_fast(__uint_as_float(cur[8 * p + 2 * e])),
-                                silu_fast(__uint_as_float(cur[8 * p + 2 * e + 1])));
-            *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
       {  // pre-load the unit with b2: every GEMM2 MMA accumulates, so the issuers need no ordering
         uint32_t bv[32];
 #pragma unroll
@@ -521,7 +537,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         e2_dispatch(n, taddr, bias, t_oi, out, agg_ld);
         if (lane == 0 && q == 0) TE_STAMP(12 + 4 * u4);
         tc_fence_before_sync();
-        if (has_next) init_unit(buf ^ 1, g.seg_n[next % g.n_tiles]);
+        if (has_next) clear_unit();
         if (lane == 0 && q == 0) TE_STAMP(13 + 4 * u4);
       }
       dlt[0] = dlt_next[0]; dlt[1] = dlt_next[1]; dlt[2] = dlt_next[2];
