@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
   } else {
     // ---------------- epilogue (16 warps) ----------------
     // A warp may only read the TMEM lane quarter warp % 4; the four warps of a quarter split the
-    // 256 columns.  Each warp pulls its 32 x 64 block into registers, hands the accumulator back
-    // to the MMA warp at once, and then writes the block out through its staging rows.
+    // 256 columns.  Each warp pulls its 32 x 64 block into registers in two halves (the accumulator
+    // goes back to the MMA warp after the second) and writes them out through its staging rows.
     const int q = warp & 3, cgrp = (warp - 2) >> 2;
     float *stg = reinterpret_cast<float *>(smem + TL_STAGES * TL_STAGE_BYTES) + (warp - 2) * (32 * TL_PITCH);
     const int orow = lane >> 3, ocol = (lane & 7) * 4;             // output pass: 4 rows x 128 B per instruction
@@ -160,46 +160,61 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
       mbar_wait(acc_full(buf), (tl >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * TL_NB + cgrp * 64;
-      uint32_t acc[2][32];
-      tmem_ld32(taddr, acc[0]);
-      tmem_ld32(taddr + 32, acc[1]);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(buf));
       const int64_t crow = (r0 + orow) * g.ldc, rrow = (r0 + orow) * g.ldr;
       __half *c16p = g.C16 ? g.C16 + (int64_t)mt * TL_BM * g.c16_kt + (q * 32 + orow) * 8 : nullptr;
 #pragma unroll
       for (int hb = 0; hb < 2; hb++) {
+        const int col = n0 + hb * 32 + ocol;
+        const bool use_gb = g.gbias != nullptr && col < g.gcols;
+        // the residual rows (or, without a residual, the per-crystal bias rows) of this pass are
+        // fetched before the transposition, so that their latency is not paid store by store
+        // (the residual aliases C: the compiler cannot move these loads above the stores itself)
+        const bool pre_res = g.residual != nullptr;
+        float4 pre[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; itr++) {
+          const int rr = itr * 4 + orow;
+          int gsrc = 0;
+          if (g.gbias != nullptr) gsrc = __shfl_sync(0xffffffffu, gi, rr);
+          pre[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < nvalid) {
+            if (pre_res) pre[itr] = *reinterpret_cast<const float4 *>(g.residual + rrow + (int64_t)itr * 4 * g.ldr + col);
+            else if (use_gb) pre[itr] = *reinterpret_cast<const float4 *>(g.gbias + (int64_t)gsrc * g.gld + col);
+          }
+        }
+        uint32_t acc[32];
+        tmem_ld32(taddr + hb * 32, acc);
+        tmem_ld_wait();
+        if (hb == 1) {                                             // the accumulator goes back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(buf));
+        }
         __syncwarp();                                              // previous output pass has drained the staging rows
 #pragma unroll
         for (int j = 0; j < 8; j++)
           *reinterpret_cast<uint4 *>(stg + lane * TL_PITCH + 4 * j) =
-              make_uint4(acc[hb][4 * j], acc[hb][4 * j + 1], acc[hb][4 * j + 2], acc[hb][4 * j + 3]);
+              make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         __syncwarp();
-        const int col = n0 + hb * 32 + ocol;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias != nullptr) b4 = *reinterpret_cast<const float4 *>(g.bias + col);
-        const bool use_gb = g.gbias != nullptr && col < g.gcols;
         const int c16 = g.c16_k0 + col;
         __half *c16c = c16p ? c16p + (int64_t)(c16 >> 3) * (TL_BM * 8) + (c16 & 7) : nullptr;
 #pragma unroll
         for (int itr = 0; itr < 8; itr++) {
           const int rr = itr * 4 + orow;
           int gsrc = 0;
-          if (g.gbias != nullptr) gsrc = __shfl_sync(0xffffffffu, gi, rr);
+          if (g.gbias != nullptr && pre_res) gsrc = __shfl_sync(0xffffffffu, gi, rr);
           if (rr < nvalid) {
             float4 x = *reinterpret_cast<const float4 *>(stg + rr * TL_PITCH + ocol);
             x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
             if (use_gb) {
-              const float4 t4 = *reinterpret_cast<const float4 *>(g.gbias + (int64_t)gsrc * g.gld + col);
+              float4 t4 = pre[itr];
+              if (pre_res) t4 = *reinterpret_cast<const float4 *>(g.gbias + (int64_t)gsrc * g.gld + col);
               x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
             }
             if (g.silu) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
-            if (g.residual != nullptr) {
-              const float4 t4 = *reinterpret_cast<const float4 *>(g.residual + rrow + (int64_t)itr * 4 * g.ldr + col);
-              x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
-            }
+            if (pre_res) { x.x += pre[itr].x; x.y += pre[itr].y; x.z += pre[itr].z; x.w += pre[itr].w; }
             if (g.C != nullptr) *reinterpret_cast<float4 *>(g.C + crow + (int64_t)itr * 4 * g.ldc + col) = x;
             if (c16c != nullptr)
               *reinterpret_cast<uint2 *>(c16c + itr * 32) = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
