@@ -50,6 +50,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single-thread roles on
+// the critical path (MMA issuers, weight loader), where the wake-up latency of try_wait matters.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 28)) {
+      printf("cb2: mbarrier spin wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+
 // ---- proxies / fences --------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {

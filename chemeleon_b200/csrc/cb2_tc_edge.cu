@@ -47,6 +47,14 @@ constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
 static_assert(TE_SMEM <= 232448, "shared memory budget");
 static_assert(TE_NCH2 >= TE_NISSUE, "every issuer must own a stage of every output unit");
 
+// single-thread roles on the critical path poll their barriers (see mbar_wait_spin)
+#define MBAR_WAIT_CRIT mbar_wait_spin
+#ifdef CB2_SPIN_WORKERS
+#define MBAR_WAIT_WORKER mbar_wait_spin
+#else
+#define MBAR_WAIT_WORKER mbar_wait
+#endif
+
 __host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
 
 __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
@@ -140,7 +148,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
   if constexpr (N == 0) {
     const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
     const uint4 *tj = reinterpret_cast<const uint4 *>(t_oj);
-    mbar_wait(acc1_full, parity);
+    MBAR_WAIT_WORKER(acc1_full, parity);
     tc_fence_after_sync();
 #pragma unroll 1
     for (int cb = 0; cb < 4; cb++) {
@@ -178,7 +186,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
     uint32_t cur = t_oj[0];
 #pragma unroll
     for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
-    mbar_wait(acc1_full, parity);
+    MBAR_WAIT_WORKER(acc1_full, parity);
     tc_fence_after_sync();
     // 16-column TMEM loads, double-buffered: the load of block hb+1 is in flight while block hb
     // goes through the SiLU (register budget: 2 x 16 accumulators + P_i / P_j values)
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       uint32_t use[TE_WSTAGES + TE_WEXTRA] = {0, 0, 0, 0, 0};
       uint32_t it = 0;
       auto load_stage = [&](int st, const __half *src) {
-        mbar_wait(w_empty(st), (use[st] & 1) ^ 1);
+        MBAR_WAIT_CRIT(w_empty(st), (use[st] & 1) ^ 1);
         mbar_arrive_expect_tx(w_full(st), TE_W_BYTES);
         bulk_g2s(w_addr(st), src, TE_W_BYTES, w_full(st));
         use[st]++;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         for (int kc = 0; kc < TE_NCH1; kc++) {       // GEMM1: five stages
           const int st = kc % (TE_WSTAGES + TE_WEXTRA);
           if (st >= TE_WSTAGES && !a1_dead) {         // the extra stages alias a1 of the previous item
-            mbar_wait(acc2_full(3), (it - 1) & 1);
+            MBAR_WAIT_CRIT(acc2_full(3), (it - 1) & 1);
             a1_dead = true;
           }
           load_stage(st, g.w_fd_t + (int64_t)kc * (TE_W_BYTES / 2));
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       auto uses_per_item = [](int st) { return st == 0 ? 11u : st < 3 ? 10u : st == 3 ? 5u : 4u; };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         if (ii == 0) TE_STAMP(0);
-        for (int u = 0; u < 4; u++) mbar_wait(acc_init(u), it & 1);   // the units hold P_i + P_j
+        for (int u = 0; u < 4; u++) MBAR_WAIT_CRIT(acc_init(u), it & 1);   // the units hold P_i + P_j
         tc_fence_after_sync();
         if (ii == 0) TE_STAMP(1);
         // GEMM1: U_m += W_fd[m] emb^T, all four units per K chunk
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         for (int kc = 0; kc < TE_NCH1; kc++) {
           if (kc % TE_NISSUE != ii) continue;
           const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
-          mbar_wait(a_full(as), (it * 3 + (kc >> 3)) & 1);
-          mbar_wait(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
+          MBAR_WAIT_CRIT(a_full(as), (it * 3 + (kc >> 3)) & 1);
+          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int j = 0; j < 2; j++) {
@@ -361,14 +369,14 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         umma_commit(acc1_full);          // count TE_NISSUE: complete when every issuer's GEMM1 MMAs are done
         if (ii == 0) TE_STAMP(2);
         // GEMM2: U_m' += W2[m'] a1^T (units pre-loaded with b2), unit after unit
-        mbar_wait(a1_ready, it & 1);
+        MBAR_WAIT_CRIT(a1_ready, it & 1);
         tc_fence_after_sync();
         if (ii == 0) TE_STAMP(3);
 #pragma unroll
         for (int c2 = 0; c2 < 4 * TE_NCH2; c2++) {
           if (c2 % TE_NISSUE != ii) continue;
           const int u = c2 / TE_NCH2, kc = c2 % TE_NCH2, ws = c2 % TE_WSTAGES;
-          mbar_wait(w_full(ws), (it * uses_per_item(ws) + 5 + c2 / TE_WSTAGES) & 1);
+          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + 5 + c2 / TE_WSTAGES) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       if (next + (int)gridDim.x < n_items) fetch_rows(next + gridDim.x);
       // ---- E2: agg_i = mean_j SiLU(U + b2); then the unit is re-initialised for the next item ----
       {
-        mbar_wait(acc2_full(u4), it & 1);
+        MBAR_WAIT_WORKER(acc2_full(u4), it & 1);
         tc_fence_after_sync();
         if (lane == 0 && q == 0) TE_STAMP(11 + 4 * u4);
         e2_dispatch(n, taddr, bias, t_oi, out, agg_ld);
