@@ -240,7 +240,7 @@ __device__ __forceinline__ void store_row_half_panel(__half *__restrict__ base, 
   }
 }
 
-__global__ void __launch_bounds__(256) k_film_apply(const float *__restrict__ y, float *__restrict__ h,
+__global__ void __launch_bounds__(256, 3) k_film_apply(const float *__restrict__ y, float *__restrict__ h,
                                                     const float *__restrict__ cond,
                                                     const int32_t *__restrict__ node2graph,
                                                     const float *__restrict__ fg, const float *__restrict__ fb,
@@ -253,22 +253,27 @@ __global__ void __launch_bounds__(256) k_film_apply(const float *__restrict__ y,
   if (row >= rows) return;
   float v[16];
   if (cond != nullptr) {
-    load_row(y + row * H, v, lane);
-    ln_row(v, fg, fb, lane);
-    int vv = (int)(row / N);
-    int n = (int)(row % N);
-    const float *cs = cond + ((int64_t)vv * B + node2graph[n]) * H2;
+    // every global load of the row is issued before the first reduction (the per-crystal FiLM
+    // row hangs off the node2graph load: fetch that one first)
+    const int gidx = node2graph[(int)(row % N)];
     float hv[16];
+    load_row(y + row * H, v, lane);
     load_row(h + row * H, hv, lane);
+    const float *cs = cond + ((row / N) * B + gidx) * H2;
+    float4 sc[4], sh[4];
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
-      int c = (lane + 32 * q4) * 4;
-      float4 sc = *reinterpret_cast<const float4 *>(cs + c);
-      float4 sh = *reinterpret_cast<const float4 *>(cs + H + c);
-      v[q4 * 4 + 0] = silu_exact(v[q4 * 4 + 0] * sc.x + sh.x) + hv[q4 * 4 + 0];
-      v[q4 * 4 + 1] = silu_exact(v[q4 * 4 + 1] * sc.y + sh.y) + hv[q4 * 4 + 1];
-      v[q4 * 4 + 2] = silu_exact(v[q4 * 4 + 2] * sc.z + sh.z) + hv[q4 * 4 + 2];
-      v[q4 * 4 + 3] = silu_exact(v[q4 * 4 + 3] * sc.w + sh.w) + hv[q4 * 4 + 3];
+      const int c = (lane + 32 * q4) * 4;
+      sc[q4] = *reinterpret_cast<const float4 *>(cs + c);
+      sh[q4] = *reinterpret_cast<const float4 *>(cs + H + c);
+    }
+    ln_row(v, fg, fb, lane);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      v[q4 * 4 + 0] = silu_exact(v[q4 * 4 + 0] * sc[q4].x + sh[q4].x) + hv[q4 * 4 + 0];
+      v[q4 * 4 + 1] = silu_exact(v[q4 * 4 + 1] * sc[q4].y + sh[q4].y) + hv[q4 * 4 + 1];
+      v[q4 * 4 + 2] = silu_exact(v[q4 * 4 + 2] * sc[q4].z + sh[q4].z) + hv[q4 * 4 + 2];
+      v[q4 * 4 + 3] = silu_exact(v[q4 * 4 + 3] * sc[q4].w + sh[q4].w) + hv[q4 * 4 + 3];
     }
     store_row(h + row * H, v, lane);
   } else {

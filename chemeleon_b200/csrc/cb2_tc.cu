@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
         const __half *ap = g.A + (int64_t)mt * TL_BM * g.a_kt;
         for (int kc = 0; kc < nk; kc++, it++) {
           const int s = it % TL_STAGES;
-          mbar_wait(empty_bar(s), ((it / TL_STAGES) & 1) ^ 1);
+          mbar_wait_spin(empty_bar(s), ((it / TL_STAGES) & 1) ^ 1);
           const uint32_t a_s = sbase + s * TL_STAGE_BYTES, w_s = a_s + TL_A_BYTES;
           mbar_arrive_expect_tx(full_bar(s), TL_STAGE_BYTES);
           bulk_g2s(a_s, ap + (int64_t)kc * (TL_KC / 8) * (TL_BM * 8), TL_A_BYTES, full_bar(s));
@@ -122,11 +122,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
         const int buf = tl & 1;
-        mbar_wait(acc_empty(buf), ((tl >> 1) & 1) ^ 1);
+        mbar_wait_spin(acc_empty(buf), ((tl >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         for (int kc = 0; kc < nk; kc++, it++) {
           const int s = it % TL_STAGES;
-          mbar_wait(full_bar(s), (it / TL_STAGES) & 1);
+          mbar_wait_spin(full_bar(s), (it / TL_STAGES) & 1);
           tc_fence_after_sync();
           const uint32_t a_s = sbase + s * TL_STAGE_BYTES, w_s = a_s + TL_A_BYTES;
 #pragma unroll
