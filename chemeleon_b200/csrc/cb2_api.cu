@@ -24,8 +24,9 @@ int launch_film_cond(const float *time_table, const float *text_part, const int3
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
-int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *out16, int64_t rows,
+int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, int64_t rows,
                      cudaStream_t st);
+int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_out, cudaStream_t st);
 int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
 int launch_edge_embed(const float *x, const int32_t *ei, const int32_t *ej, float *emb, int64_t n_rows,
                       cudaStream_t st);
@@ -181,8 +182,11 @@ static int decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_for
     CB2_TRY(tc_forward_layers(m, b, io, w, st));
   }
   float *hf = io->node_features ? io->node_features : w.hf;
-  CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, nullptr, VN, st));
-  {
+  const bool tc_heads = io->precision != CB2_PRECISION_FP32 && m->w_head_t != nullptr;
+  CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, VN, st));
+  if (tc_heads) {   // cat16 is dead after the last layer: it carries the hi | lo split of the features
+    CB2_TRY(tc_head(m, w.cat16, VN, io->head_out, st));
+  } else {
     GemmEpilogue e;
     e.bias = m->b_head;
     CB2_TRY(launch_sgemm_nt(hf, H, m->w_head, io->head_out, HEADC, VN, HEADC, H, e, st));

@@ -298,10 +298,13 @@ int launch_film_apply(const float *y, float *h, const float *cond, const int32_t
   return CB2_OK;
 }
 
-// plain LayerNorm rows (final_layer_norm, cspnet.py:385-386)
+// plain LayerNorm rows (final_layer_norm, cspnet.py:385-386).  split16 (tensor-core path): the
+// normalised row is also written as two fp16 terms hi + lo (hi = fp16(x), lo = fp16(x - hi)) into
+// a 1024-column row-panel buffer, hi at columns 0:512 and lo at 512:1024 -- the A operand of the
+// split-precision head GEMM (three fp16 products reproduce the fp32 product to ~2^-22).
 __global__ void __launch_bounds__(256) k_layernorm(const float *__restrict__ x, const float *__restrict__ g,
                                                    const float *__restrict__ b, float *__restrict__ out,
-                                                   __half *__restrict__ out16, int64_t rows) {
+                                                   __half *__restrict__ split16, int64_t rows) {
   int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -309,13 +312,19 @@ __global__ void __launch_bounds__(256) k_layernorm(const float *__restrict__ x, 
   load_row(x + row * H, v, lane);
   ln_row(v, g, b, lane);
   if (out != nullptr) store_row(out + row * H, v, lane);
-  if (out16 != nullptr) store_row_half(out16 + row * H, v, lane);
+  if (split16 != nullptr) {
+    float lo[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) lo[q] = v[q] - __half2float(__float2half_rn(fminf(fmaxf(v[q], -65504.f), 65504.f)));
+    store_row_half_panel(split16, row, H2, v, lane);
+    store_row_half_panel(split16 + (H / 8) * 1024, row, H2, lo, lane);
+  }
 }
 
-int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *out16, int64_t rows,
+int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, int64_t rows,
                      cudaStream_t st) {
   if (rows == 0) return CB2_OK;
-  k_layernorm<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, b, out, out16, rows);
+  k_layernorm<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, b, out, split16, rows);
   CB2_LAUNCH_OK("k_layernorm");
   return CB2_OK;
 }

@@ -57,6 +57,9 @@ struct TcLinearArgs {
   const float *gbias;     // per-crystal additive term, row r uses gbias[gidx[r % gmod]][c] for c < gcols
   const int32_t *gidx;
   int gmod, gcols, gld;
+  int a_wrap;             // > 0: K chunk kc reads A chunk kc % a_wrap (A sections reused along K)
+  int n_store;            // columns >= n_store are computed but not stored (0 = Nw)
+  const float *out_scale; // device scalar multiplied into the accumulator before the bias (NULL = 1)
 };
 
 __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
@@ -106,7 +109,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
           mbar_wait_spin(empty_bar(s), ((it / TL_STAGES) & 1) ^ 1);
           const uint32_t a_s = sbase + s * TL_STAGE_BYTES, w_s = a_s + TL_A_BYTES;
           mbar_arrive_expect_tx(full_bar(s), TL_STAGE_BYTES);
-          bulk_g2s(a_s, ap + (int64_t)kc * (TL_KC / 8) * (TL_BM * 8), TL_A_BYTES, full_bar(s));
+          const int ka = g.a_wrap > 0 ? kc % g.a_wrap : kc;
+          bulk_g2s(a_s, ap + (int64_t)ka * (TL_KC / 8) * (TL_BM * 8), TL_A_BYTES, full_bar(s));
 #pragma unroll
           for (int k8 = 0; k8 < TL_KC / 8; k8++)
             bulk_g2s(w_s + k8 * (TL_NB * 16), g.Wt + ((int64_t)(kc * (TL_KC / 8) + k8) * g.Nw + n0) * 8, TL_NB * 16,
@@ -149,12 +153,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
     const int q = warp & 3, cgrp = (warp - 2) >> 2;
     float *stg = reinterpret_cast<float *>(smem + TL_STAGES * TL_STAGE_BYTES) + (warp - 2) * (32 * TL_PITCH);
     const int orow = lane >> 3, ocol = (lane & 7) * 4;             // output pass: 4 rows x 128 B per instruction
+    const int n_store = g.n_store > 0 ? g.n_store : g.Nw;
+    const float oscale = g.out_scale ? __ldg(g.out_scale) : 1.0f;
     int tl = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
       const int buf = tl & 1;
       const int mt = t / n_nt, n0 = (t % n_nt) * TL_NB + cgrp * 64;
       const int64_t r0 = (int64_t)mt * TL_BM + q * 32;             // first row of this warp
-      const int nvalid = (int)(g.M - r0 < 32 ? g.M - r0 : 32);
+      // rows past M and column blocks past n_store are computed by the MMA but never touched here
+      const int nvalid = n0 >= n_store ? 0 : (int)(g.M - r0 < 32 ? g.M - r0 : 32);
       int gi = 0;
       if (g.gbias != nullptr && lane < nvalid) gi = g.gidx[(r0 + lane) % g.gmod];
       mbar_wait(acc_full(buf), (tl >> 1) & 1);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
               make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         __syncwarp();
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr) b4 = *reinterpret_cast<const float4 *>(g.bias + col);
+        if (g.bias != nullptr && nvalid > 0) b4 = *reinterpret_cast<const float4 *>(g.bias + col);
         const int c16 = g.c16_k0 + col;
         __half *c16c = c16p ? c16p + (int64_t)(c16 >> 3) * (TL_BM * 8) + (c16 & 7) : nullptr;
 #pragma unroll
@@ -207,7 +214,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
           if (g.gbias != nullptr && pre_res) gsrc = __shfl_sync(0xffffffffu, gi, rr);
           if (rr < nvalid) {
             float4 x = *reinterpret_cast<const float4 *>(stg + rr * TL_PITCH + ocol);
-            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            x.x = fmaf(x.x, oscale, b4.x); x.y = fmaf(x.y, oscale, b4.y);
+            x.z = fmaf(x.z, oscale, b4.z); x.w = fmaf(x.w, oscale, b4.w);
             if (use_gb) {
               float4 t4 = pre[itr];
               if (pre_res) t4 = *reinterpret_cast<const float4 *>(g.gbias + (int64_t)gsrc * g.gld + col);
@@ -242,8 +250,9 @@ static int num_sms(int *out) {
 
 int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
   if (a.M == 0) return CB2_OK;
-  if (a.K % TL_KC != 0 || a.K <= 0 || a.Nw % TL_NB != 0 || a.a_kt % 8 != 0 || a.K > a.a_kt)
-    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, a_kt%8 must be 0 and K <= a_kt");
+  if (a.K % TL_KC != 0 || a.K <= 0 || a.Nw % TL_NB != 0 || a.a_kt % 8 != 0 || (a.a_wrap == 0 && a.K > a.a_kt) ||
+      a.a_wrap * TL_KC > a.a_kt || (a.n_store % 64) != 0)
+    return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, a_kt%8, n_store%64 must be 0 and K <= a_kt");
   static bool attr_set = false;
   if (!attr_set) {
     CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
@@ -329,6 +338,18 @@ int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x
   e.agg16 = agg16; e.ld_agg = ld_agg; e.agg_col = agg_col; e.agg_kt = agg_kt; e.N = b->n_nodes; e.V = b->n_variants;
   e.n_tiles = b->n_tiles;
   return launch_tc_edge(e, sms, st);
+}
+
+// Output heads (type_out | coord_out, cspnet.py:388-401) in split precision: A = [hi | lo | hi] of
+// the final LayerNorm (k_layernorm wrote hi | lo into cat16, the hi section is read twice),
+// W image = s [w_hi | w_hi | w_lo] with a power-of-two scale s that keeps w_lo out of the fp16
+// subnormals; the blob starts with 1/s.  hi w_hi + lo w_hi + hi w_lo = x w (1 + O(2^-22)).
+int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_out, cudaStream_t st) {
+  TcLinearArgs a{};
+  a.A = split16; a.a_kt = H2; a.a_wrap = H2 / TL_KC; a.M = VN; a.K = 3 * H;
+  a.Wt = (const __half *)m->w_head_t + 8; a.Nw = 256; a.out_scale = (const float *)m->w_head_t;
+  a.C = head_out; a.ldc = HEADC; a.n_store = HEADC; a.bias = m->b_head;
+  return launch_tc_linear(a, st);
 }
 
 // One CSPNet trunk pass on the tensor cores.  fp32 row-major: h (residual stream), y, P;

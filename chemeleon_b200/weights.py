@@ -204,6 +204,24 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
             return None
         return d(torch.cat([tile_k_major(t[i:i + rows]) for i in range(0, t.shape[0], rows)], dim=0))
 
+    def head_split_image(w: Tensor) -> Optional[Tensor]:
+        """Operand blob of the split-precision head GEMM: 16-byte header (float32 1/s) followed by
+        the K-major image of s*[w_hi | w_hi | w_lo] padded to 256 rows ([192][256][8] fp16).  The
+        power-of-two scale s keeps w_lo = s*w - w_hi out of the fp16 subnormals."""
+        if not tensor_core:
+            return None
+        wmax = float(w.abs().max())
+        s = 2.0 ** math.floor(math.log2(1024.0 / wmax)) if wmax > 0 else 1.0
+        ws = w.double() * s
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.double()).to(torch.float16)
+        full = torch.zeros(256, 3 * w.shape[1], dtype=torch.float16)
+        full[: w.shape[0]] = torch.cat([hi, hi, lo], dim=1)
+        blob = torch.zeros(8 + full.numel(), dtype=torch.float16)
+        blob[:2].view(torch.float32)[0] = 1.0 / s
+        blob[8:] = tile_k_major(full).reshape(-1)
+        return d(blob)
+
     w_cond = get("decoder.film_layer.mlp_cond.0.weight")  # [1024, time_dim(+text_dim)]
     b_cond = get("decoder.film_layer.mlp_cond.0.bias")
     te = schedules.time_embedding_table(cfg.timesteps, cfg.time_dim)  # [T+1,128]
@@ -254,7 +272,7 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
         film_w_text=d(w_text) if w_text is not None else None, film_b_cond=d(b_cond),
         layers=layers, final_g=d(get("decoder.final_layer_norm.weight")),
         final_b=d(get("decoder.final_layer_norm.bias")),
-        w_head=d(w_head), b_head=d(b_head), w_head_t=tiled(w_head),
+        w_head=d(w_head), b_head=d(b_head), w_head_t=head_split_image(w_head),
         w_lat=d(get("decoder.lattice_out.weight")), sigmas_norm=sn,
         q_mats=sd.get("d3pm.q_mats"), q_one_step_mats=sd.get("d3pm.q_one_step_mats"),
         extra={"film_w_cond": d(w_cond)})

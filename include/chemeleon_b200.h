@@ -91,7 +91,8 @@ typedef struct {
   const float *final_b;
   const float *w_head;          /* [128,512] rows 0:104 type_out.weight, 104:107 coord_out.weight */
   const float *b_head;          /* [128] */
-  const void *w_head_t;
+  const void *w_head_t;         /* tensor-core heads (may be NULL: fp32 SIMT heads): 16-byte header {float 1/s}, then the
+                                 * fp16 K-major image [192][256][8] of s*[w_hi | w_hi | w_lo] (split precision, rows >= 128 zero) */
   const float *w_lat;           /* [9,512] lattice_out.weight */
 } cb2_model;
 
@@ -187,7 +188,7 @@ int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bia
 
 /* C = act(A16 W16^T + bias) on the tensor cores (tcgen05, fp32 accumulate).  A16: fp16
  * row-major [M,lda]; Wt: fp16 operand image [K/8][Nw][8] of a torch Linear weight [Nw,K]
- * (weights.tile_k_major); K % 32 == 0, Nw % 256 == 0.  The building block of the
+ * (weights.tile_k_major); K % 64 == 0, Nw % 256 == 0, lda % 8 == 0 (A is re-tiled into the row-panel layout of the pipeline first).  The building block of the
  * node-level GEMMs (FilmLayer.proj, hoisted W1 blocks, node_mlp; cspnet.py:86,113,120). */
 int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
                   int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream);
