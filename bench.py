@@ -50,6 +50,20 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def profiled_traffic(name: str = "r1_k_tc_edge_full.txt"):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed summary of
+    the `ncu --set full` capture under profiles/ (None if the summary is missing)."""
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None
+    tot = 0.0
+    for line in open(p):
+        f = line.split()
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
+    return tot or None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -284,8 +298,11 @@ def main():
         ach = flops / (ms_edge * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "k_tc_edge (one CSPLayer edge model, cond+null)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": f"{peaks['source']} cuBLAS bf16 burst (fp16 tcgen05 runs at the bf16 rate)",
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": profiled_traffic(),
+                "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1_k_tc_edge_full.txt)",
+                "peak_source": f"{peaks['source']} cuBLAS bf16 burst (fp16 tcgen05 runs at the bf16 rate; "
+                               "the kernel is timed alone)",
+                "frac_of_sustained_peak": ach / peaks.get("bf16_tflops_sustained", peak),
                 "ms_per_launch": ms_edge, "launches_per_step": 12,
                 "share_of_step": 12 * ms_edge / ms_step}
     step_flops = 4 * B * forward_flops(n)

@@ -12,7 +12,7 @@ def launches(path, out):
         d = agg.setdefault(name, [0, 0.0]); d[0] += 1; d[1] += v; tot += v
     with open(out, 'w') as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph`\n")
-        f.write("# (4 sampler timesteps + the standalone edge-layer timing loop; per-launch times are cold-cache and serialised: compare SHARES)\n")
+        f.write("# (the first 110 launches: one decoder forward and a half; per-launch times are cold-cache and serialised: compare SHARES)\n")
         f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg ms':>9s} {'share':>7s}\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:58]:58s} {c:8d} {t:10.3f} {t/c:9.4f} {100*t/tot:6.1f}%\n")
@@ -27,13 +27,13 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__inst_executed.sum', 'sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active',
         'l1tex__t_sector_hit_rate.pct', 'sm__cycles_elapsed.avg', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 
-def full(rep, out, title):
+def full(rep, out, title, index=0):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = r[0], r[1], r[2]
+    hdr, units, vals = r[0], r[1], r[2 + index]
     d = dict(zip(hdr, zip(units, vals)))
     with open(out, 'w') as f:
-        f.write(f"# {title}\n# ncu --set full --clock-control none --import-source on (one launch)\n")
+        f.write(f"# {title}\n# ncu --set full --clock-control none --import-source on (launch {index} of the capture)\n")
         for k in ['Kernel Name'] + KEYS:
             if k in d:
                 f.write(f"{k:72s} {d[k][0]:16s} {d[k][1]}\n")
@@ -43,6 +43,10 @@ def full(rep, out, title):
             f.write(f"{h:72s} {v:.3f}\n")
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches_r1.csv", "profiles/r1_launches.txt")
-    full("gpurun_out/edge_full_r1.ncu-rep", "profiles/r1_k_tc_edge_full.txt", "k_tc_edge, C3 (B=4096, n=20, cond+null), one CSPLayer")
-    full("gpurun_out/linear_full_r1.ncu-rep", "profiles/r1_k_tc_linear_full.txt", "k_tc_linear, first launch of a C3 step (FiLM projection, M=163840 N=512 K=512)")
+    launches("gpurun_out/launches_q.csv", "profiles/r1_launches.txt")
+    rep = "gpurun_out/full_r1b.ncu-rep"   # -k regex:k_tc_(edge|linear) -s 5 -c 5: one CSPLayer of a C3 forward
+    full(rep, "profiles/r1_k_tc_edge_full.txt", "k_tc_edge, C3 (B=4096, n=20, cond+null), one CSPLayer", 2)
+    full(rep, "profiles/r1_k_tc_linear_full.txt", "k_tc_linear, FiLM projection of a C3 forward (M=163840 N=512 K=512)", 0)
+    full(rep, "profiles/r1_k_tc_linear_hoist_full.txt", "k_tc_linear, hoisted [W_hi;W_hj] GEMM (M=163840 N=1024 K=512, per-crystal bias)", 1)
+    full(rep, "profiles/r1_k_tc_linear_mlp1_full.txt", "k_tc_linear, node MLP layer 1 (M=163840 N=512 K=1024, SiLU, fp16 panel output)", 3)
+    full(rep, "profiles/r1_k_tc_linear_mlp2_full.txt", "k_tc_linear, node MLP layer 2 (M=163840 N=512 K=512, SiLU + residual, fp32 + fp16 outputs)", 4)
