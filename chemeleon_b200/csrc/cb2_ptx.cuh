@@ -70,6 +70,65 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
+// ---- thread-block clusters (CTA pairs of the shared-GEMM1 edge kernel) ----------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// arrive (release at cluster scope) on an mbarrier of any CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// polling wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ void mbar_wait_spin_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 28)) {
+      printf("cb2: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) {
+      printf("cb2: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---- proxies / fences --------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -153,6 +212,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+
+// ... and on the barrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 
 __device__ __forceinline__ float tanh_approx(float x) {
