@@ -308,6 +308,8 @@ int launch_film_apply(const float *y, float *h, const float *cond, const int32_t
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
 int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
+int launch_tc_film(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *film_cond,
+                   const __half *h16, float *h, __half *cat16, int n_sm, cudaStream_t st);
 
 // C-ABI unit entry: row-major fp16 A; the row-panel copy the kernel reads is made here.
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
@@ -360,18 +362,30 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
   const int64_t VN = (int64_t)V * N;
   if (!m->film_wp_t) return fail(CB2_ERR_BAD_ARG, "tensor-core path needs the fp16 operand images (pack with tensor_core=True)");
   if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
+  static int fused_film = -1;       // CB2_FILM_FUSED=0: separate FiLM GEMM + k_film_apply (A-B knob)
+  if (fused_film < 0) {
+    const char *e = getenv("CB2_FILM_FUSED");
+    fused_film = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  int sms = 0;
+  CB2_TRY(num_sms(&sms));
   for (int li = 0; li < m->n_layers; li++) {
     const cb2_layer_weights &L = m->layers[li];
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
-    if (io->film_cond != nullptr) {
-      TcLinearArgs a{};
-      a.A = w.h16; a.a_kt = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
-      a.C = w.y; a.ldc = H; a.bias = m->film_bp;
-      CB2_TRY(launch_tc_linear(a, st));
+    if (io->film_cond != nullptr && fused_film) {
+      // FiLM projection + LN + FiLM + SiLU + residual + layer LN in one kernel (y stays in TMEM)
+      CB2_TRY(launch_tc_film(m, L, b, io->film_cond, w.h16, w.h, w.cat16, sms, st));
+    } else {
+      if (io->film_cond != nullptr) {
+        TcLinearArgs a{};
+        a.A = w.h16; a.a_kt = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
+        a.C = w.y; a.ldc = H; a.bias = m->film_bp;
+        CB2_TRY(launch_tc_linear(a, st));
+      }
+      CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
+                                nullptr, 0, w.cat16, 0, H2, N, B, V, st));
     }
-    CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
-                              nullptr, 0, w.cat16, 0, H2, N, B, V, st));
     CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
     {
       TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T  (+ lattice term + b1 on the P_i half)
