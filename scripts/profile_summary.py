@@ -43,10 +43,10 @@ def full(rep, out, title, index=0):
             f.write(f"{h:72s} {v:.3f}\n")
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches_q.csv", "profiles/r1_launches.txt")
-    rep = "gpurun_out/full_r1b.ncu-rep"   # -k regex:k_tc_(edge|linear) -s 5 -c 5: one CSPLayer of a C3 forward
-    full(rep, "profiles/r1_k_tc_edge_full.txt", "k_tc_edge, C3 (B=4096, n=20, cond+null), one CSPLayer", 2)
-    full(rep, "profiles/r1_k_tc_linear_full.txt", "k_tc_linear, FiLM projection of a C3 forward (M=163840 N=512 K=512)", 0)
-    full(rep, "profiles/r1_k_tc_linear_hoist_full.txt", "k_tc_linear, hoisted [W_hi;W_hj] GEMM (M=163840 N=1024 K=512, per-crystal bias)", 1)
-    full(rep, "profiles/r1_k_tc_linear_mlp1_full.txt", "k_tc_linear, node MLP layer 1 (M=163840 N=512 K=1024, SiLU, fp16 panel output)", 3)
-    full(rep, "profiles/r1_k_tc_linear_mlp2_full.txt", "k_tc_linear, node MLP layer 2 (M=163840 N=512 K=512, SiLU + residual, fp32 + fp16 outputs)", 4)
+    launches("gpurun_out/launches_r1.csv", "profiles/r1_launches.txt")
+    rep = "gpurun_out/full_r1c.ncu-rep"   # -k regex:k_tc_(edge|linear|film) -s 4 -c 5: MLP2 of one layer, then the next CSPLayer
+    full(rep, "profiles/r1_k_tc_edge_full.txt", "k_tc_edge, C3 (B=4096, n=20, cond+null), one CSPLayer", 3)
+    full(rep, "profiles/r1_k_tc_film_full.txt", "k_tc_film, fused FiLM projection + FiLM + residual + LayerNorms (M=163840, N=K=512)", 1)
+    full(rep, "profiles/r1_k_tc_linear_hoist_full.txt", "k_tc_linear, hoisted [W_hi;W_hj] GEMM (M=163840 N=1024 K=512, per-crystal bias)", 2)
+    full(rep, "profiles/r1_k_tc_linear_mlp1_full.txt", "k_tc_linear, node MLP layer 1 (M=163840 N=512 K=1024, SiLU, fp16 panel output)", 4)
+    full(rep, "profiles/r1_k_tc_linear_mlp2_full.txt", "k_tc_linear, node MLP layer 2 (M=163840 N=512 K=512, SiLU + residual, fp32 + fp16 outputs)", 0)
