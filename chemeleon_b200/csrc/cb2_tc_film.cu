@@ -10,7 +10,7 @@
 // LayerNorms are row-local: y never goes to HBM (the unfused pair wrote and re-read it:
 // 0.67 GB of 1.67 GB per layer at C3).  Persistent, one CTA per SM:
 //   warp 0   : loader (bulk copies: one 8 KB block of the row-panel A operand + one 32 KB
-//              block of the weight image per K chunk of 32, 3-stage ring)
+//              block of the weight image per K chunk of 32, 4-stage ring)
 //   warp 1   : MMA issue (M128 N256 K16 x 2 column halves), TMEM alloc
 //   warps 2-17: epilogue; warp = (lane quarter q, column group of 128).  TMEM hands every
 //              thread one row, so the row statistics are in-thread sums plus one exchange
@@ -30,13 +30,13 @@ namespace cb2 {
 
 using namespace ptx;
 
-constexpr int TF_KC = 32, TF_STAGES = 3;
+constexpr int TF_KC = 32, TF_STAGES = 4;
 constexpr int TF_A_BYTES = 128 * TF_KC * 2;           // 8 KB
 constexpr int TF_W_BYTES = H * TF_KC * 2;             // 32 KB: [4 k8][512 rows][16 B]
 constexpr int TF_STAGE_BYTES = TF_A_BYTES + TF_W_BYTES;
-constexpr int TF_PITCH = 36;
+constexpr int TF_PITCH = 20;                         // floats per staged row: 16 columns + 4 pad (conflict-free row reads)
 constexpr int TF_STG_OFF = TF_STAGES * TF_STAGE_BYTES;
-constexpr int TF_STG_BYTES = 16 * 32 * TF_PITCH * 4;  // one 32 x 32 fp32 block per epilogue warp
+constexpr int TF_STG_BYTES = 16 * 32 * TF_PITCH * 4;  // one 32 x 16 fp32 block per epilogue warp
 constexpr int TF_PAR_OFF = TF_STG_OFF + TF_STG_BYTES; // bias, g1, b1, g2, b2: 5 x 512 floats
 constexpr int TF_PART_OFF = TF_PAR_OFF + 5 * H * 4;   // [2 passes][4 column groups][128 rows] float2
 constexpr int TF_BAR_OFF = TF_PART_OFF + 2 * 4 * 128 * 8;
