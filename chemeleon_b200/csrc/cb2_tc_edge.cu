@@ -43,6 +43,7 @@ constexpr int TE_THREADS = TE_WORKERS + 32 * (TE_NISSUE + 1);
 
 constexpr int TE_NCH1 = DIS / TE_KC;            // 24 stages of K=32
 constexpr int TE_NCH2 = 4;                      // per output unit: 4 stages of K=128
+constexpr int TE_DEFER = 4;                     // GEMM1 chunks issued for units 0..2 before unit 3 is clear (<= 5 W stages)
 constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
 static_assert(TE_SMEM <= 232448, "shared memory budget");
 static_assert(TE_NCH2 >= TE_NISSUE, "every issuer must own a stage of every output unit");
@@ -343,26 +344,53 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       auto uses_per_item = [](int st) { return st == 0 ? 11u : st < 3 ? 10u : st == 3 ? 5u : 4u; };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         if (ii == 0) TE_STAMP(0);
-        for (int u = 0; u < 4; u++) MBAR_WAIT_CRIT(acc_init(u), it & 1);   // the units hold P_i + P_j
+        // Units 0..2 are cleared long before unit 3 (the last one GEMM2 completes, its E2 is the
+        // tail of the previous item): the first TE_DEFER chunks are issued for units 0..2 only, their
+        // unit-3 MMAs follow once unit 3 is clear (the chunks' slots and stages are held until then;
+        // the rings are deep enough: 8 slots, 5 stages).
+        for (int u = 0; u < 3; u++) MBAR_WAIT_CRIT(acc_init(u), it & 1);
         tc_fence_after_sync();
         if (ii == 0) TE_STAMP(1);
-        // GEMM1: U_m += W_fd[m] emb^T, all four units per K chunk
-#pragma unroll
-        for (int kc = 0; kc < TE_NCH1; kc++) {
-          if (kc % TE_NISSUE != ii) continue;
-          const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
-          MBAR_WAIT_CRIT(a_full(as), (it * 3 + (kc >> 3)) & 1);
-          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
-          tc_fence_after_sync();
+        auto g1_mmas = [&](int as, int ws, int m_lo, int m_hi) {
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             const uint64_t bd = d_lbo2k + (uint64_t)((as * TE_A_BYTES + 2 * j * 2048) >> 4);
 #pragma unroll
             for (int m = 0; m < 4; m++) {
+              if (m < m_lo || m >= m_hi) continue;
               const uint64_t ad = d_lbo8k + (uint64_t)((w_off(ws) + 2 * j * 8192 + m * 2048) >> 4);
               umma_f16(tmem + m * 128, ad, bd, idesc_kk, 1u);
             }
           }
+        };
+        // GEMM1: U_m += W_fd[m] emb^T
+#pragma unroll
+        for (int kc = 0; kc < TE_DEFER; kc++) {
+          if (kc % TE_NISSUE != ii) continue;
+          const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
+          MBAR_WAIT_CRIT(a_full(as), (it * 3 + (kc >> 3)) & 1);
+          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
+          tc_fence_after_sync();
+          g1_mmas(as, ws, 0, 3);
+        }
+        MBAR_WAIT_CRIT(acc_init(3), it & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kc = 0; kc < TE_DEFER; kc++) {
+          if (kc % TE_NISSUE != ii) continue;
+          const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
+          g1_mmas(as, ws, 3, 4);
+          umma_commit(a_empty(as));
+          umma_commit(w_empty(ws));
+        }
+#pragma unroll
+        for (int kc = TE_DEFER; kc < TE_NCH1; kc++) {
+          if (kc % TE_NISSUE != ii) continue;
+          const int as = (kc & 3) + 4 * ((kc >> 2) & 1), ws = kc % NS;
+          MBAR_WAIT_CRIT(a_full(as), (it * 3 + (kc >> 3)) & 1);
+          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + kc / NS) & 1);
+          tc_fence_after_sync();
+          g1_mmas(as, ws, 0, 4);
           umma_commit(a_empty(as));
           umma_commit(w_empty(ws));
         }
