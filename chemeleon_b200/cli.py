@@ -62,7 +62,7 @@ def sample_prompt(text_input, n_samples, n_atoms, save_dir, checkpoint_dir, prec
 @click.option("--n-samples", default=100, type=int)
 @click.option("--max-natoms", default=40, type=int)
 @click.option("--max-factor", default=13, type=int)
-@click.option("--reduced-natoms", default=None, type=int, help="atoms in the reduced formula (needs pymatgen if omitted)")
+@click.option("--reduced-natoms", default=None, type=int, help="atoms in the reduced formula (default: from the formula)")
 @click.option("-s", "--save-dir", default="results/composition")
 @click.option("--checkpoint-dir", default=None)
 @click.option("--precision", default="tc", type=click.Choice(["tc", "fp32"]))
@@ -70,14 +70,19 @@ def sample_composition(target_composition, n_samples, max_natoms, max_factor, re
                        checkpoint_dir, precision):
     """All Z-factor buckets are sampled as ONE ragged batch (the reference runs them one after the other)."""
     if reduced_natoms is None:
-        from pymatgen.core import Composition  # pragma: no cover
+        from .validity import reduced_formula_counts
 
-        reduced_natoms = int(Composition(target_composition).reduced_composition.num_atoms)
+        reduced_natoms = sum(reduced_formula_counts(target_composition))
     model = _load("composition", checkpoint_dir, precision)
     natoms = [reduced_natoms * f for f in range(1, max_factor + 1) if reduced_natoms * f <= max_natoms
               for _ in range(n_samples)]
     click.echo(f"Sampling {len(natoms)} structures for {target_composition} in one ragged batch...")
-    _save(model.sample_batch(natoms, [target_composition] * len(natoms)), Path(save_dir))
+    # validity check of the reference (lattice <= 60 A, reduced composition == target;
+    # sample_target_composition.py:57-62) on the device
+    valid, flags = model.sample_batch_valid(natoms, [target_composition] * len(natoms),
+                                            target_composition=target_composition, min_distance=0.0)
+    click.echo(f"{len(valid)} of {len(natoms)} structures pass the lattice-length / composition filter")
+    _save(valid, Path(save_dir))
     click.echo(f"Results saved in {save_dir}")
 
 

@@ -26,6 +26,9 @@ int launch_film_apply(const float *y, float *h, const float *cond, const int32_t
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
 int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, int64_t rows,
                      cudaStream_t st);
+int launch_validity(const int64_t *a, const float *x, const float *lat, const int32_t *graph_off, int B,
+                    const int32_t *target, float max_len, float thr, int32_t *flags, float *min_dist,
+                    float *max_abc, cudaStream_t st);
 int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_out, cudaStream_t st);
 int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
 int launch_edge_embed(const float *x, const int32_t *ei, const int32_t *ej, float *emb, int64_t n_rows,
@@ -209,6 +212,17 @@ int cb2_abi_version(void) { return CB2_ABI_VERSION; }
 const char *cb2_last_error(void) { return g_err.c_str(); }
 
 uint64_t cb2_launch_count(void) { return g_launches.load(); }
+
+int cb2_validity_filter(const int64_t *atom_types, const float *frac_coords, const float *lattices,
+                        const int32_t *graph_off, int32_t n_graphs, const int32_t *target_reduced_counts,
+                        float max_length, float min_distance, int32_t *flags, float *min_dist, float *max_abc,
+                        void *stream) {
+  if (n_graphs < 0) return fail(CB2_ERR_BAD_ARG, "validity_filter: negative n_graphs");
+  if (n_graphs > 0 && (!atom_types || !frac_coords || !lattices || !graph_off || !flags || !min_dist || !max_abc))
+    return fail(CB2_ERR_BAD_ARG, "validity_filter: null argument");
+  return launch_validity(atom_types, frac_coords, lattices, graph_off, n_graphs, target_reduced_counts, max_length,
+                         min_distance, flags, min_dist, max_abc, (cudaStream_t)stream);
+}
 
 /* development aid (not part of the documented ABI): clock64 timeline of the edge kernel's CTA 0 */
 int cb2_debug_edge_timeline(long long *out96) { return debug_edge_timeline(out96); }

@@ -339,3 +339,21 @@ class ChemeleonB200:
             text_embeds, null_text_embeds = self._embed_texts(texts)
         a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed)
         return self._to_atoms(a, x, l, [int(n) for n in natoms])
+
+    def sample_batch_valid(self, natoms: Sequence[int], texts: Optional[Sequence[str]] = None, *,
+                           target_composition: Optional[str] = None, max_length: float = 60.0,
+                           min_distance: float = 0.5, **kw):
+        """`sample_batch` followed by the reference's validity filters, evaluated on the device
+        (scripts/evaluate.py:177-189, sample_target_composition.py:57-62; see validity.py).
+        Returns (atoms of the structures that pass, flags int32[B] of all structures)."""
+        from .validity import validity_flags
+
+        natoms = [int(n) for n in natoms]
+        text_embeds, null_text_embeds = kw.pop("text_embeds", None), kw.pop("null_text_embeds", None)
+        if self.text_guide and text_embeds is None:
+            text_embeds, null_text_embeds = self._embed_texts(texts)
+        a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, **kw)
+        flags, _, _ = validity_flags(a, x, l, natoms, target_composition, max_length, min_distance)
+        flags = flags.cpu()
+        atoms = self._to_atoms(a, x, l, natoms)
+        return [at for at, f in zip(atoms, flags.tolist()) if f == 0], flags

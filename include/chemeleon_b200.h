@@ -221,6 +221,20 @@ int cb2_update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *
 int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const cb2_step_args *a,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Validity pre-filter of finished structures on the device: restates
+ * chemeleon/scripts/evaluate.py:177-189 (max(lattice.abc) > max_length; smallest positive
+ * periodic distance < min_distance) and sample_target_composition.py:57-62 (reduced
+ * composition != target).  graph_off: [n_graphs+1] node offsets; target_reduced_counts: [104]
+ * atoms per atomic number of the target's reduced formula, or NULL to skip that test.
+ * flags[g] = OR of CB2_INVALID_*; min_dist[g] (inf if no positive distance), max_abc[g]. */
+#define CB2_INVALID_LATTICE 1
+#define CB2_INVALID_DISTANCE 2
+#define CB2_INVALID_COMPOSITION 4
+int cb2_validity_filter(const int64_t *atom_types, const float *frac_coords, const float *lattices,
+                        const int32_t *graph_off, int32_t n_graphs, const int32_t *target_reduced_counts,
+                        float max_length, float min_distance, int32_t *flags, float *min_dist, float *max_abc,
+                        void *stream);
+
 /* Number of kernels launched by this library in this process (bench: gpu_launches). */
 uint64_t cb2_launch_count(void);
 
