@@ -230,7 +230,7 @@ def main():
     def time_edge_kernel(reps: int = 6) -> float:
         """ms per launch of the edge kernel alone (one CSPLayer, both variants), CUDA events on its stream."""
         topo = run.topo
-        P = torch.randn(topo.V * N, 1024, device=dev)
+        P = torch.randn(topo.V * N, 1024, device=dev).half()
         agg = torch.empty(topo.V * N, 512, device=dev, dtype=torch.float16)
 
         def edge_once():

@@ -48,7 +48,7 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
                      int64_t ldc, int64_t M, int K, int silu, cudaStream_t st);
 int debug_edge_timeline(long long *out96);
-int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
+int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P, __half *agg16,
                   int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
 
 size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) {
@@ -279,7 +279,7 @@ int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, cons
 }
 
 int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
-                   const float *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   const void *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
                    size_t workspace_bytes, void *stream) {
   CB2_TRY(check_model(m));
   CB2_TRY(check_batch(b, precision));
@@ -291,10 +291,10 @@ int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const 
     ForwardWs fw;
     carve_forward(a, b, precision, fw);
     if (!workspace || !a.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
-    return f32_edge_layer(L, b, frac_coords, P, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
+    return f32_edge_layer(L, b, frac_coords, (const float *)P, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
   }
   if (!L.w_fd_t || !L.w2_t) return fail(CB2_ERR_BAD_ARG, "edge_layer: fp16 operand images missing");
-  return tc_edge_layer(L, b, frac_coords, P, (__half *)agg, ld_agg, 0, 0, (cudaStream_t)stream);
+  return tc_edge_layer(L, b, frac_coords, (const __half *)P, (__half *)agg, ld_agg, 0, 0, (cudaStream_t)stream);
 }
 
 int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, void *workspace,

@@ -50,6 +50,8 @@ struct TcLinearArgs {
   int64_t ldc;
   __half *C16;        // fp16 row-panel output (optional): c16_kt columns per panel, written at [c16_k0, c16_k0+Nw)
   int c16_kt, c16_k0;
+  __half *C16r;       // fp16 row-major output (optional), leading dimension ldc16r
+  int64_t ldc16r;
   const float *bias;
   int silu;
   const float *residual;
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
             if (g.silu) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
             if (pre_res) { x.x += pre[itr].x; x.y += pre[itr].y; x.z += pre[itr].z; x.w += pre[itr].w; }
             if (g.C != nullptr) *reinterpret_cast<float4 *>(g.C + crow + (int64_t)itr * 4 * g.ldc + col) = x;
+            if (g.C16r != nullptr)
+              *reinterpret_cast<uint2 *>(g.C16r + (r0 + rr) * g.ldc16r + col) = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
             if (c16c != nullptr)
               *reinterpret_cast<uint2 *>(c16c + itr * 32) = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
           }
@@ -330,7 +334,7 @@ int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const
   return rc;
 }
 
-int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P, __half *agg16,
+int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P, __half *agg16,
                   int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st) {
   int sms = 0;
   CB2_TRY(num_sms(&sms));
@@ -390,11 +394,11 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
     {
       TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T  (+ lattice term + b1 on the P_i half)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
-      a.C = w.P; a.ldc = H2;
+      a.C16r = reinterpret_cast<__half *>(w.P); a.ldc16r = H2;   // fp16: the edge kernel gathers half the bytes
       a.gbias = w.cg; a.gidx = b->node2graph; a.gmod = N; a.gcols = H; a.gld = H;
       CB2_TRY(launch_tc_linear(a, st));
     }
-    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, w.P, w.cat16, 0, H, H2, st));
+    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P), w.cat16, 0, H, H2, st));
     {
       TcLinearArgs a{};   // z = SiLU([hn|agg] Wn1^T + bn1)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;

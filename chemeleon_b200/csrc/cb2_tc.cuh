@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t silu2_half(float a, float b) {
 }
 
 struct TcEdgeArgs {
-  const float *P;          // [V*N,1024] hoisted terms (P_i + lattice term + b1 | P_j)
+  const __half *P;         // [V*N,1024] fp16 row-major hoisted terms (P_i + lattice term + b1 | P_j)
   const float *x;          // [N,3]
   const int32_t *row_i;    // [n_tiles*128] node i of the tile's edge row, -1 = padding
   const int32_t *row_j;

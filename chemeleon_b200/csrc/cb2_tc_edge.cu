@@ -144,7 +144,7 @@ __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, c
 // per crystal (they repeat for every segment of the same crystal).  N == 0: generic version, two
 // gathers per edge.
 template <int N>
-__device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint32_t *t_oi, const uint32_t *t_oj,
+__device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, const uint32_t *t_oi, const uint32_t *t_oj,
                                      uint8_t *a1_dst, uint32_t acc1_full, uint32_t parity) {
   if constexpr (N == 0) {
     const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
@@ -162,7 +162,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
         const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
         const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) pv[j4 * 4 + k] = Pc[ois[k] == TE_PAD ? 0u : ois[k]] + Pc[ojs[k]];
+        for (int k = 0; k < 4; k++) pv[j4 * 4 + k] = __half2float(Pc[ois[k] == TE_PAD ? 0u : ois[k]]) + __half2float(Pc[ojs[k]]);
       }
       tmem_ld_wait();
 #pragma unroll
@@ -181,12 +181,12 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
 #pragma unroll
     for (int sgm = 0; sgm < S; sgm++) {
       const uint32_t oi = t_oi[sgm * N];
-      piv[sgm] = Pc[oi == TE_PAD ? 0u : oi];
+      piv[sgm] = __half2float(Pc[oi == TE_PAD ? 0u : oi]);
     }
     float pj[N];
     uint32_t cur = t_oj[0];
 #pragma unroll
-    for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
+    for (int k = 0; k < N; k++) pj[k] = __half2float(Pc[cur + (uint32_t)k * (uint32_t)H2]);
     MBAR_WAIT_WORKER(acc1_full, parity);
     tc_fence_after_sync();
     // 16-column TMEM loads, double-buffered: the load of block hb+1 is in flight while block hb
@@ -210,7 +210,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
             if (oj0 != cur) {
               cur = oj0;
 #pragma unroll
-              for (int k = 0; k < N; k++) pj[k] = Pc[cur + (uint32_t)k * (uint32_t)H2];
+              for (int k = 0; k < N; k++) pj[k] = __half2float(Pc[cur + (uint32_t)k * (uint32_t)H2]);
             }
           }
           x[j] += piv[e / N] + pj[e % N];
@@ -227,7 +227,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const float *Pc, const uint
   }
 }
 
-__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const float *Pc, const uint32_t *t_oi,
+__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half *Pc, const uint32_t *t_oi,
                                             const uint32_t *t_oj, uint8_t *a1_dst, uint32_t acc1_full,
                                             uint32_t parity) {
   switch (n) {
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     const int r = q * 32 + lane;                 // edge row owned while producing the embedding
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + u4 * 128;
     const int c = u4 * 128 + q * 32 + lane;      // output channel owned in the epilogues
-    const float *Pc = g.P + c;
+    const __half *Pc = g.P + c;
     const float bias = __ldg(g.b2 + c);
     const int oc = g.agg_col + c;
     __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
         if (o != TE_PAD) {
           const char *pp = reinterpret_cast<const char *>(g.P + o);
 #pragma unroll
-          for (int l = 0; l < 16; l++) prefetch_l2(pp + l * 128);
+          for (int l = 0; l < 8; l++) prefetch_l2(pp + l * 128);
         }
       }
     };
@@ -770,7 +770,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TE_THREADS, 1) k_tc_
     const uint32_t taddr_x = tmem + ((uint32_t)(q * 32) << 16) + e1_m * 128;
     const uint32_t taddr_o = tmem + ((uint32_t)(q * 32) << 16) + u4 * 128;
     const int c_in = q * 32 + lane;                                  // channel within a 128-channel unit
-    const float *Pc = g.P + (size_t)e1_v * (size_t)g.N * H2 + 256 * rank + e1_m * 128 + c_in;
+    const __half *Pc = g.P + (size_t)e1_v * (size_t)g.N * H2 + 256 * rank + e1_m * 128 + c_in;
     const float bias_o = __ldg(g.b2 + u4 * 128 + c_in);              // b2 of the O unit this thread handles in E2
     const float bias_x = __ldg(g.b2 + e1_m * 128 + c_in);            // b2 of O_{m'} (pre-loaded over X_{m'})
     const int oc = g.agg_col + u4 * 128 + c_in;
@@ -814,7 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TE_THREADS, 1) k_tc_
       if (o != TE_PAD) {
         const char *pp = reinterpret_cast<const char *>(g.P + (size_t)(sel >> 1) * (size_t)g.N * H2 + o);
 #pragma unroll
-        for (int l = 0; l < 16; l++) prefetch_l2(pp + l * 128);
+        for (int l = 0; l < 8; l++) prefetch_l2(pp + l * 128);
       }
     };
     auto fill_unit = [&](uint32_t ta, int c0, int ncol, uint32_t val) {   // tcgen05.st of a constant

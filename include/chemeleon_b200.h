@@ -196,9 +196,10 @@ int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, cons
 /* Edge model + scatter_mean of ONE CSPLayer (CSPLayer.edge_model + the aggregation in
  * node_model, cspnet.py:129-160) from the hoisted node terms P [V*N,1024] = (P_i | P_j):
  *   agg_i = mean_j SiLU(W2 SiLU(P_i[i] + P_j[j] + W_fd emb(x_j - x_i)) + b2).
- * precision FP32: agg is float [V*N, ld_agg]; TC_F16: agg is fp16 [V*N, ld_agg]. */
+ * precision FP32: P and agg are float; TC_F16: P and agg are fp16 (row-major, leading dimensions
+ * 1024 and ld_agg). */
 int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
-                   const float *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   const void *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
                    size_t workspace_bytes, void *stream);
 
 /* One CSPNet.forward (cspnet.py:345-405) for all V variants of the batch. */

@@ -16,7 +16,7 @@ eng = DecoderEngine(random_init_state_dict(cfg, seed=4), cfg, precision="tc")
 topo = BatchTopology([n] * B, 2, "cuda", exact=False, tensor_core=True)
 N = topo.N
 x = torch.rand(N, 3, device="cuda")
-P = torch.randn(2 * N, 1024, device="cuda")
+P = torch.randn(2 * N, 1024, device="cuda").half()
 agg = torch.empty(2 * N, 512, device="cuda", dtype=torch.float16)
 def once():
     _lib.check(eng.lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), agg.data_ptr(),

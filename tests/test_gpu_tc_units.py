@@ -60,7 +60,8 @@ def test_edge_layer_tc_vs_fp32(natoms, V):
     _lib.check(lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), agg32.data_ptr(),
                                   512, 0, ws.data_ptr(), ws.numel(), _stream()), "edge fp32")
     agg16 = torch.full((V * N, 512), float("nan"), device="cuda", dtype=torch.float16)
-    _lib.check(lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), agg16.data_ptr(),
+    P16 = P.half()                      # tensor-core mode gathers the hoisted terms as fp16
+    _lib.check(lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P16.data_ptr(), agg16.data_ptr(),
                                   512, 1, None, 0, _stream()), "edge tc")
     torch.cuda.synchronize()
     assert torch.isfinite(agg16).all()
@@ -91,7 +92,7 @@ for natoms in ([4, 7, 5, 1, 40, 33], [20] * 300):
     topo = BatchTopology(natoms, 2, "cuda", exact=False, tensor_core=True)
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(topo.N, 3, generator=g) * 2 - 0.5).cuda()
-    P = torch.randn(2 * topo.N, 1024, generator=g).cuda()
+    P = torch.randn(2 * topo.N, 1024, generator=g).cuda().half()
     agg = torch.full((2 * topo.N, 512), float("nan"), device="cuda", dtype=torch.float16)
     _lib.check(eng.lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), agg.data_ptr(),
                                       512, 1, None, 0, torch.cuda.current_stream().cuda_stream), "edge")
