@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone edge-kernel timing (profiling runs)")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(0, args.warmup)
 
@@ -249,7 +250,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms_edge_alone = time_edge_kernel() if args.precision == "tc" else None
+    ms_edge_alone = time_edge_kernel() if args.precision == "tc" and not args.no_roofline else None
     c0 = int(lib.cb2_launch_count())
     run.capture()
     launches_per_step = (int(lib.cb2_launch_count()) - c0) // (2 if run.use_cuda_graph else 1) if run.use_cuda_graph \
@@ -297,7 +298,7 @@ def main():
     # ---------------- dominant kernel (roofline) ----------------
     peaks = measured_peaks()
     roof = None
-    if args.precision == "tc":
+    if args.precision == "tc" and not args.no_roofline:
         ms_hot = time_edge_kernel()          # again, right after the timed steps (board at its power limit)
         flops = run.topo.V * run.topo.E * EDGE_FLOP_PER_EDGE_LAYER
         ach = flops / (ms_edge_alone * 1e-3) / 1e12

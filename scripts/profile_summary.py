@@ -11,8 +11,8 @@ def launches(path, out):
         v = v / 1e6 if u == 'ns' else v / 1e3 if u == 'us' else v * 1e3 if u == 's' else v
         d = agg.setdefault(name, [0, 0.0]); d[0] += 1; d[1] += v; tot += v
     with open(out, 'w') as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph`\n")
-        f.write("# (the first 110 launches: the 8 stand-alone edge-kernel launches of the roofline timing, then one decoder forward and a half; per-launch times are cold-cache and serialised: compare SHARES)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-roofline`\n")
+        f.write("# (the first 110 launches: two decoder forwards and a bit; per-launch times are cold-cache and serialised: compare SHARES)\n")
         f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg ms':>9s} {'share':>7s}\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:58]:58s} {c:8d} {t:10.3f} {t/c:9.4f} {100*t/tot:6.1f}%\n")
