@@ -244,6 +244,14 @@ __device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half 
   }
 }
 
+// Note on mbarrier parities: a wait only compares one parity bit, so a thread that asks for phase
+// k+1 of a barrier whose phase k is still pending sees "completed".  Every waiter here is therefore
+// kept within one phase of its barrier: ring slots/stages that are waited for by DIFFERENT issuer
+// threads from one use to the next are only reached after the previous use has been consumed
+// (GEMM1 weight stage kc % 5: the issuers are gated by the embedding producers, which run in
+// lockstep with the MMAs, and at the start of an item by the common wait on unit 3), and the
+// embedding slots of the pair kernel, whose period is shorter than its weight run-ahead, are always
+// waited for by the same thread.
 #define TE_WORKER_BARRIER() asm volatile("bar.sync 1, 512;" ::: "memory")
 
 // development aid: timeline of CTA 0's items 1..3 (clock64 stamps), read back by cb2_debug_edge_timeline()
