@@ -43,7 +43,10 @@ constexpr int TE_THREADS = TE_WORKERS + 32 * (TE_NISSUE + 1);
 
 constexpr int TE_NCH1 = DIS / TE_KC;            // 24 stages of K=32
 constexpr int TE_NCH2 = 4;                      // per output unit: 4 stages of K=128
-constexpr int TE_DEFER = 4;                     // GEMM1 chunks issued for units 0..2 before unit 3 is clear (<= 5 W stages)
+#ifndef CB2_TE_DEFER
+#define CB2_TE_DEFER 4
+#endif
+constexpr int TE_DEFER = CB2_TE_DEFER;                     // GEMM1 chunks issued for units 0..2 before unit 3 is clear (<= 5 W stages)
 constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
 static_assert(TE_SMEM <= 232448, "shared memory budget");
 static_assert(TE_NCH2 >= TE_NISSUE, "every issuer must own a stage of every output unit");
