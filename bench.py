@@ -174,9 +174,10 @@ def main():
         sample = (f"{args.cpu_batch} crystals x {K} timesteps of the same workload (4 CSPNet forwards + update per "
                   f"timestep), extrapolated to 1000 homogeneous timesteps")
         line = {"impl": "reference", "metric": "structures/sec (1000-step sampling, 20-atom cells)", "value": v,
-                "unit": "structures/s", "n_gpus": 0, "steps": K, "warmup": W, "ms_per_step": dt * 1e3,
+                "unit": "structures/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": K, "warmup": W,
+                "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": dict(config, batch_per_gpu=args.cpu_batch),
+                "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "structures/s", "cores": cores, "kind": "port",
                                  "sample": sample},
                 "e2e": {"value": v, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
