@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the B200 sampler on BASELINE.json's metric.
+"""Benchmark of the B200 sampler on BASELINE.json's metric and configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3|c4|c5]
 
-Metric: structures/sec for 1000-step sampling of 20-atom cells (BASELINE config
-"mp-40-style synthetic text prompts, 20-atom cells, batch 4096, 1000 steps on 1xB200").
+Metric: structures/sec for 1000-step sampling.  The default workload is BASELINE config 3
+("mp-40-style synthetic text prompts, 20-atom cells, batch 4096, 1000 steps on 1xB200"); the other
+BASELINE configs are selected with --config:
 
-A bench "step" is ONE reverse-diffusion timestep over the whole batch: FiLM
-conditioning, predictor forward (cond | null), predictor update, corrector forward
-(cond | null), corrector update = 4 CSPNet forwards + the state update, nothing
-skipped.  Timesteps are homogeneous in cost, so
-    structures/s = n_gpus * batch / (ms_per_step * 1e-3 * 1000 timesteps).
-`value` is measured with the state resident in HBM (CUDA-graph replays, CUDA events);
-`e2e` goes through the public API (`ChemeleonB200.sample_states`) with the text
-embeddings in pinned host memory and the finished structures copied back to the host
-inside the timed region.  Multi-GPU: samples are sharded by sample (weak scaling, fixed
-batch per GPU), no data-path collective; the final all-gather of structures is part of e2e.
+    c1  3 x 6-atom cells (the reference's own CPU-runnable case): launch-latency bound
+    c2  TiO2 composition sweep: 13 Z-factor buckets (n = 3..39) x 100 samples as ONE ragged batch
+    c3  4096 x 20-atom cells PER GPU (weak scaling; the driver's default)
+    c4  16384 x 40-atom cells in total, STRONG-scaled over the ranks
+    c5  16384 ragged cells, n ~ U[4, 40] (seed 3), ~30 distinct prompts, strong-scaled (LPT partition)
+
+A bench "step" is ONE reverse-diffusion timestep over the whole batch: FiLM conditioning, predictor
+forward (cond | null), predictor update, corrector forward (cond | null), corrector update = 4 CSPNet
+forwards + the state update, nothing skipped.  Timesteps are homogeneous in cost, so
+    structures/s = total crystals / (ms_per_step * 1e-3 * 1000 timesteps).
+Every rank runs the PRODUCT multi-GPU path (`chemeleon_b200.dist`: LPT partition of the global batch,
+Philox noise keyed by global sample id, NCCL all-gather of the finished structures at the end).
+`value` is measured with the state resident in HBM (CUDA-graph replays, CUDA events, max over ranks);
+`e2e` is a K-timestep job through the public API (`dist.sample_sharded` + the `ase.Atoms` boundary) with
+the text embeddings in pinned host memory, the all-gather, the device->host copy of the structures and
+their conversion to Atoms objects inside the timed region.
 """
 from __future__ import annotations
 
@@ -34,11 +41,42 @@ if ROOT not in sys.path:
 T_STEPS = 1000
 EDGE_FLOP_PER_EDGE_LAYER = 2 * 768 * 512 + 2 * 512 * 512          # 1 310 720
 NODE_FLOP_PER_NODE_LAYER = 524288 + 1048576 + 1572864              # 3 145 728
+EDGE_PROFILE = "r2_edge_full.txt"                                  # ncu --set full summary under profiles/
 
 
 def forward_flops(n: int, layers: int = 6) -> float:
     """Algorithmic FLOPs of one CSPNet forward for one crystal of n atoms."""
     return layers * (EDGE_FLOP_PER_EDGE_LAYER * n * n + NODE_FLOP_PER_NODE_LAYER * n) + 109568 * n + 1.3e6
+
+
+def workload(config: str, world: int, batch: int, natoms: int):
+    """(global natoms list, prompt id per sample, n_prompts, description, scaling)."""
+    import numpy as np
+
+    if config == "c1":
+        nat = [6] * 3
+        return nat, [0] * 3, 1, "config 1: 'LiMnO4 orthorhombic', n_atoms=6, n_samples=3 (latency case)", "replicas"
+    if config == "c2":
+        nat = [3 * f for f in range(1, 14) for _ in range(100)]
+        return nat, [0] * len(nat), 1, ("config 2: composition TiO2, n_samples=100, max_natoms=40: the 13 Z-factor "
+                                        "buckets (n = 3..39) as ONE ragged batch"), "strong"
+    if config == "c3":
+        nat = [natoms] * (batch * world)
+        rng = np.random.RandomState(5)
+        return nat, rng.randint(0, 64, len(nat)).tolist(), 64, (
+            f"mp-40-style synthetic prompts, {natoms}-atom cells, batch {batch} per GPU, 1000-step sampler "
+            f"(CFG cond_scale 2.0, predictor-corrector)"), "weak"
+    if config == "c4":
+        nat = [40] * 16384
+        rng = np.random.RandomState(5)
+        return nat, rng.randint(0, 64, len(nat)).tolist(), 64, (
+            "config 4: 40-atom cells (1600 edges/crystal), batch 16384 in total, sharded by sample"), "strong"
+    if config == "c5":
+        rng = np.random.RandomState(3)
+        nat = rng.randint(4, 41, 16384).tolist()
+        return nat, rng.randint(0, 30, len(nat)).tolist(), 30, (
+            "config 5: chemical-system sweep Li-Mn-O, 16384 ragged cells n ~ U[4,40] (seed 3), 30 prompts, CFG"), "strong"
+    raise ValueError(config)
 
 
 def measured_peaks():
@@ -50,18 +88,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def profiled_traffic(name: str = "r1_k_tc_edge_full.txt"):
+def profiled_traffic(name: str = EDGE_PROFILE):
     """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed summary of
     the `ncu --set full` capture under profiles/ (None if the summary is missing)."""
-    p = os.path.join(ROOT, "profiles", name)
-    if not os.path.exists(p):
-        return None
-    tot = 0.0
-    for line in open(p):
-        f = line.split()
-        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(f[2]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
-    return tot or None
+    for cand in (name, "r1_k_tc_edge_full.txt"):
+        p = os.path.join(ROOT, "profiles", cand)
+        if not os.path.exists(p):
+            continue
+        tot = 0.0
+        for line in open(p):
+            f = line.split()
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
+        if tot:
+            return tot, cand
+    return None, None
 
 
 class ClockSampler:
@@ -111,7 +152,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(batch: int, natoms: int, steps: int, warmup: int = 1):
+def cpu_sample_natoms(config: str, natoms: int, cpu_batch: int):
+    """Bounded sample of the workload for the CPU arm (about 10-30 s of host work)."""
+    if config == "c1":
+        return [6] * 3
+    if config == "c2":
+        return [3, 12, 21, 30, 39]
+    if config == "c4":
+        return [40] * max(1, cpu_batch // 4)
+    if config == "c5":
+        import numpy as np
+
+        return np.random.RandomState(3).randint(4, 41, 16384)[:cpu_batch].tolist()
+    return [natoms] * cpu_batch
+
+
+def cpu_reference_run(nat, steps: int, warmup: int = 1):
     """The reference's CPU algorithm (oracle restatement, validated bit-for-bit against the
     unmodified reference in the build container) on this box's host cores.  Returns
     (structures_per_sec, seconds_per_step, cores)."""
@@ -126,8 +182,7 @@ def cpu_reference_run(batch: int, natoms: int, steps: int, warmup: int = 1):
     cfg = SamplerConfig()
     sd = random_init_state_dict(cfg, seed=0, head_scale=0.01, lattice_identity=True)
     so = O.SamplerOracle(sd, sd["sigma_scheduler.sigmas_norm"])
-    nat = [natoms] * batch
-    N = natoms * batch
+    batch, N = len(nat), sum(nat)
     g = torch.Generator().manual_seed(1)
     text = torch.randn(batch, cfg.text_dim, generator=g)
     null = torch.randn(1, cfg.text_dim, generator=g)
@@ -146,38 +201,53 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
-    ap.add_argument("--batch", type=int, default=4096, help="crystals per GPU")
-    ap.add_argument("--natoms", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=4096, help="c3: crystals per GPU")
+    ap.add_argument("--natoms", type=int, default=20, help="c3: atoms per cell")
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone edge-kernel timing (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (profiling runs)")
+    ap.add_argument("--single-cta-edge", action="store_true", help="A/B: one-CTA edge kernel instead of the CTA-pair kernel")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(0, args.warmup)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"mp-40-style synthetic prompts, {args.natoms}-atom cells, batch {args.batch} per GPU, "
-                f"1000-step sampler (CFG cond_scale 2.0, predictor-corrector)")
-    config = {"workload": workload, "batch_per_gpu": args.batch, "natoms": args.natoms, "timesteps": T_STEPS,
-              "forwards_per_step": 4, "sharding": f"by sample, {world} rank(s), no data-path collective",
-              "step": "one reverse-diffusion timestep over the batch; value = gpus*batch/(ms_per_step*1e-3*1000)",
-              "l2": "working set (>2.5 GB of activations per forward) is far larger than the 126 MB L2"}
+    nat_global, prompt_ids, n_prompts, desc, scaling = workload(args.config, world, args.batch, args.natoms)
+    metric = "structures/sec (1000-step sampling, 20-atom cells)" if args.config == "c3" and args.natoms == 20 else \
+        f"structures/sec (1000-step sampling, config {args.config})"
+    config = {"workload": desc, "config": args.config, "crystals_total": len(nat_global),
+              "atoms_total": int(sum(nat_global)), "timesteps": T_STEPS, "forwards_per_step": 4,
+              "sharding": f"by sample, {world} rank(s), LPT partition, no data-path collective; one all-gather of the "
+                          f"finished structures (inside e2e)",
+              "step": "one reverse-diffusion timestep over the batch; value = crystals/(ms_per_step*1e-3*1000)",
+              "l2": "working set (>2.5 GB of activations per forward at c3) is far larger than the 126 MB L2"}
+    if args.config == "c3":
+        config.update(batch_per_gpu=args.batch, natoms=args.natoms)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        v, dt, cores = cpu_reference_run(args.cpu_batch, args.natoms, K, max(1, min(W, 1)))
-        sample = (f"{args.cpu_batch} crystals x {K} timesteps of the same workload (4 CSPNet forwards + update per "
-                  f"timestep), extrapolated to 1000 homogeneous timesteps")
-        line = {"impl": "reference", "metric": "structures/sec (1000-step sampling, 20-atom cells)", "value": v,
+        nat = cpu_sample_natoms(args.config, args.natoms, args.cpu_batch)
+        v, dt, cores = cpu_reference_run(nat, K, max(1, min(W, 1)))
+        sample = (f"{len(nat)} crystals (atoms per cell: {sorted(set(nat))}) x {K} timesteps of the same workload "
+                  f"(4 CSPNet forwards + update per timestep), extrapolated to 1000 homogeneous timesteps")
+        # the config block says what RAN on the CPU: a bounded sample, not the GPU arm's batch
+        cfg_ref = dict(config, workload=desc + f" -- CPU arm: bounded sample of {len(nat)} crystals",
+                       crystals_total=len(nat), atoms_total=int(sum(nat)), cpu_batch=len(nat),
+                       sharding="none (host CPU, all cores, rank 0 only)")
+        if args.config == "c3":
+            cfg_ref["batch_per_gpu"] = len(nat)
+        line = {"impl": "reference", "metric": metric, "value": v,
                 "unit": "structures/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": K, "warmup": W,
                 "ms_per_step": dt * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config,
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg_ref,
                 "cpu_baseline": {"value": v, "unit": "structures/s", "cores": cores, "kind": "port",
                                  "sample": sample},
                 "e2e": {"value": v, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,13 +255,17 @@ def main():
         print(json.dumps(line))
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ctypes as C
+
     from chemeleon_b200 import _lib
+    from chemeleon_b200 import dist as cdist
     from chemeleon_b200.config import SamplerConfig
     from chemeleon_b200.sampler import ChemeleonB200
     from chemeleon_b200.weights import random_init_state_dict
@@ -200,15 +274,17 @@ def main():
     sd = random_init_state_dict(cfg, seed=0, head_scale=0.01, lattice_identity=True)
     model = ChemeleonB200(sd, cfg, device=f"cuda:{local_rank}", precision=args.precision,
                           use_cuda_graph=not args.no_graph)
+    if args.single_cta_edge:
+        model.engine.model.flags |= _lib.MODEL_EDGE_SINGLE_CTA
     lib = _lib.load()
-    B, n = args.batch, args.natoms
-    natoms = [n] * B
-    N = B * n
-    g = torch.Generator().manual_seed(1)
-    text_host = torch.randn(B, cfg.text_dim, generator=g).pin_memory()
-    null_host = torch.randn(1, cfg.text_dim, generator=g).pin_memory()
-    gid = list(range(rank * B, (rank + 1) * B))
     dev = model.device
+    Bg = len(nat_global)
+    g = torch.Generator().manual_seed(1)
+    prompts = torch.randn(n_prompts, cfg.text_dim, generator=g)       # one synthetic embedding per distinct prompt
+    text_host = prompts[torch.tensor(prompt_ids)].contiguous().pin_memory()
+    null_host = torch.randn(1, cfg.text_dim, generator=g).pin_memory()
+    plan = cdist.ShardPlan(nat_global, world, rank)
+    B, N = len(plan.my_natoms), int(sum(plan.my_natoms))
 
     def barrier():
         if world > 1:
@@ -222,22 +298,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident timing ----------------
-    run = model.make_run(natoms, text_host, null_host, 2.0, 1e-5, None, seed=1234 + 0, graph_gid=gid)
-    l_T, x_T = model.initial_noise(B, N, 1234)
-    run.init_state(l_T, x_T)
+    def all_ranks(x: float):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
-    import ctypes as C
+    # ---------------- device-resident timing (product path: this rank's shard of the global batch) ----------------
+    run = cdist.prepare_sharded_run(model, plan, text_host, null_host, 2.0, 1e-5, seed=1234)
+    topo = run.topo
 
     def time_edge_kernel(reps: int = 6) -> float:
         """ms per launch of the edge kernel alone (one CSPLayer, both variants), CUDA events on its stream."""
-        topo = run.topo
         P = torch.randn(topo.V * N, 1024, device=dev).half()
         agg = torch.empty(topo.V * N, 512, device=dev, dtype=torch.float16)
+        cg = torch.randn(topo.B, 512, device=dev)
 
         def edge_once():
             _lib.check(lib.cb2_edge_layer(C.byref(model.engine.model), 0, topo.byref(), run.x.data_ptr(), P.data_ptr(),
-                                          agg.data_ptr(), 512, 1, None, 0, torch.cuda.current_stream().cuda_stream),
+                                          cg.data_ptr(), agg.data_ptr(), 512, 1, None, 0,
+                                          torch.cuda.current_stream().cuda_stream),
                        "cb2_edge_layer")
 
         for _ in range(2):
@@ -251,11 +333,11 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms_edge_alone = time_edge_kernel() if args.precision == "tc" and not args.no_roofline else None
+    want_roof = args.precision == "tc" and not args.no_roofline and N > 0
+    ms_edge_alone = time_edge_kernel() if want_roof else None
     c0 = int(lib.cb2_launch_count())
     run.capture()
-    launches_per_step = (int(lib.cb2_launch_count()) - c0) // (2 if run.use_cuda_graph else 1) if run.use_cuda_graph \
-        else None
+    launches_per_step = (int(lib.cb2_launch_count()) - c0) // 2 if run.use_cuda_graph else None
     for _ in range(W):
         run.step()
     barrier()
@@ -269,53 +351,82 @@ def main():
         run.step()
     ev1.record()
     barrier()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / K)
+    my_ms = ev0.elapsed_time(ev1) / K
+    ms_step = max_over_ranks(my_ms)
+    rank_ms = all_ranks(my_ms)
     if launches_per_step is None:
         launches_per_step = (int(lib.cb2_launch_count()) - c1) // K
     clock_info = clocks.stop() if rank == 0 else None
     finite = bool(torch.isfinite(run.x).all() and torch.isfinite(run.l).all())
-    value = world * B / (ms_step * 1e-3 * T_STEPS)
+    value = Bg / (ms_step * 1e-3 * T_STEPS)
 
     # ---------------- end to end through the public API ----------------
-    def e2e_once(seed):
-        a, x, l = model.sample_states(natoms, text_host, null_host, 2.0, 1e-5, None, seed=seed,
-                                      t_stop=T_STEPS - K, graph_gid=gid)
-        if world > 1:
-            outs = [torch.empty_like(x) for _ in range(world)]
-            dist.all_gather(outs, x)
-        return a.to("cpu", non_blocking=False), x.to("cpu"), l.to("cpu")
+    e2e = None
+    parity = None
+    if not args.no_e2e:
+        def e2e_once(seed):
+            a, x, l = cdist.sample_sharded(model, nat_global, text_host, null_host, 2.0, 1e-5, seed=seed,
+                                           t_stop=T_STEPS - K)
+            ha, hx, hl = a.cpu(), x.cpu(), l.cpu()
+            atoms = model._to_atoms(ha, hx, hl, nat_global) if rank == 0 else None   # the ase.Atoms boundary
+            return ha, hx, hl, atoms
 
-    e2e_once(1)  # warm (run cache already holds the captured graph)
-    barrier()
-    ev0.record()
-    ha, hx, hl = e2e_once(2)
-    ev1.record()
-    barrier()
-    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / K)
-    e2e_value = world * B / (ms_e2e * 1e-3 * T_STEPS)
-    h2d = (text_host.numel() + null_host.numel()) * 4 / K
-    d2h = (ha.numel() * 8 + hx.numel() * 4 + hl.numel() * 4) / K
+        e2e_once(1)  # warm (the run cache already holds the captured graph)
+        barrier()
+        ev0.record()
+        ha, hx, hl, atoms = e2e_once(2)
+        ev1.record()
+        barrier()
+        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / K)
+        h2d = (text_host.numel() + null_host.numel()) * 4 / K
+        d2h = (ha.numel() * 8 + hx.numel() * 4 + hl.numel() * 4) / K
+        e2e = {"value": Bg / (ms_e2e * 1e-3 * T_STEPS), "unit": "structures/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+               "api": "chemeleon_b200.dist.sample_sharded + state_to_atoms (K-timestep job)"}
+        # ---- parity at scale / shard invariance: 64 crystals of the job above, re-sampled ALONE on rank 0 ----
+        if rank == 0:
+            rs = np.random.RandomState(11)
+            pick = np.sort(rs.choice(Bg, size=min(64, Bg), replace=False))
+            sub = cdist.ShardPlan([nat_global[i] for i in pick], 1, 0)
+            l_T, x_T = model.initial_noise(Bg, int(sum(nat_global)), 2)
+            nodes = torch.from_numpy(cdist.node_slices(nat_global, pick.tolist())).to(dev)
+            gi = torch.from_numpy(pick).to(dev)
+            a2, x2, l2 = model.sample_states(sub.natoms, text_host[torch.from_numpy(pick)], null_host, 2.0, 1e-5,
+                                             seed=2, t_stop=T_STEPS - K, graph_gid=pick.tolist(),
+                                             init_noise=(l_T[gi], x_T[nodes]))
+            nd = nodes.cpu()
+            types_equal = bool(torch.equal(a2.cpu(), ha[nd]))
+            dx = float(((x2.cpu() - hx[nd] + 0.5) % 1.0 - 0.5).abs().max())
+            dl = float((l2.cpu() - hl[torch.from_numpy(pick)]).abs().max() / hl.abs().max().clamp_min(1e-30))
+            parity = {"crystals": int(len(pick)), "types_equal": types_equal, "max_coord_diff": dx,
+                      "max_lattice_rel": dl, "ok": bool(types_equal and dx <= 1e-5 and dl <= 1e-5),
+                      "what": "crystals of the timed e2e job re-sampled alone on rank 0 (same global ids / noise)"}
+        barrier()
 
     # ---------------- dominant kernel (roofline) ----------------
     peaks = measured_peaks()
     roof = None
-    if args.precision == "tc" and not args.no_roofline:
+    if want_roof:
         ms_hot = time_edge_kernel()          # again, right after the timed steps (board at its power limit)
-        flops = run.topo.V * run.topo.E * EDGE_FLOP_PER_EDGE_LAYER
+        flops = topo.V * topo.E * EDGE_FLOP_PER_EDGE_LAYER
         ach = flops / (ms_edge_alone * 1e-3) / 1e12
         ach_hot = flops / (ms_hot * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": "k_tc_edge (one CSPLayer edge model, cond+null)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": profiled_traffic(),
-                "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1_k_tc_edge_full.txt)",
+        traffic, tsrc = profiled_traffic()
+        kname = "k_tc_edge" if (args.single_cta_edge or topo.V == 1) else "k_tc_edge2 (CTA pair, cta_group::2)"
+        roof = {"bound": "tensor", "kernel": f"{kname} (one CSPLayer edge model, cond+null)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_unit": f"DRAM bytes per launch at c3 (ncu --set full, profiles/{tsrc})",
+                "algorithmic_flops_per_launch": flops,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 burst (fp16 tcgen05 runs at the bf16 rate); the kernel "
                                "is timed alone on the launching stream, before the sampling steps",
                 "ms_per_launch": ms_edge_alone, "launches_per_step": 12,
                 "after_timed_steps": {"ms_per_launch": ms_hot, "achieved": ach_hot,
                                       "frac_of_sustained_peak": ach_hot / peaks.get("bf16_tflops_sustained", peak)},
-                "share_of_step": 12 * ms_hot / ms_step}
-    step_flops = 4 * B * forward_flops(n)
-    step_tflops = world * step_flops / (ms_step * 1e-3) / 1e12
+                "share_of_step": 12 * ms_hot / my_ms,
+                "tile_fill": topo.E / max(1, topo.n_tiles * 128)}
+    step_flops = 4 * sum(forward_flops(n) for n in nat_global)
+    step_tflops = step_flops / (ms_step * 1e-3) / 1e12
 
     if rank != 0:
         if world > 1:
@@ -323,24 +434,29 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, cores = cpu_reference_run(args.cpu_batch, n, args.cpu_steps)
+        nat = cpu_sample_natoms(args.config, args.natoms, args.cpu_batch)
+        v, dt, cores = cpu_reference_run(nat, args.cpu_steps)
         cpu = {"value": v, "unit": "structures/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_batch} crystals x {args.cpu_steps} timesteps of the same workload "
-                         f"({dt:.2f} s/timestep), extrapolated to 1000 homogeneous timesteps"}
+               "sample": f"{len(nat)} crystals (atoms per cell: {sorted(set(nat))}) x {args.cpu_steps} timesteps of the "
+                         f"same workload ({dt:.2f} s/timestep), extrapolated to 1000 homogeneous timesteps"}
     line = {
-        "metric": "structures/sec (1000-step sampling, 20-atom cells)", "value": value, "unit": "structures/s",
+        "metric": metric, "value": value, "unit": "structures/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": scaling, "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
         "data": "synthetic (random-init weights of the reference architecture, heads x0.01, identity lattice "
                 "head; synthetic text embeddings; in-kernel Philox noise)",
-        "config": config, "clocks": clock_info,
-        "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e},
+        "config": config, "clocks": clock_info, "e2e": e2e,
         "gpu_launches": int(launches_per_step) * K, "launches_per_step": int(launches_per_step),
         "roofline": roof, "cpu_baseline": cpu,
         "algorithmic_tflops": step_tflops, "state_finite": finite,
+        "parity_at_scale": parity, "rank_ms_per_step": rank_ms,
+        "latency_ms_per_1000_steps": ms_step * T_STEPS,
     }
+    if world > 1:
+        line["shard_invariant"] = bool(parity and parity["ok"])
+        line["partition_cost_spread"] = (max(plan.cost(r) for r in range(world)) /
+                                         max(1e-9, min(plan.cost(r) for r in range(world))))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

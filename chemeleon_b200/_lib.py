@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libchemeleon_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 16
 HIDDEN = 512
 HEAD_COLS = 128
@@ -19,6 +19,10 @@ COEF_COLS = 16
 TILE_ROWS = 128
 PRECISION_FP32 = 0
 PRECISION_TC_F16 = 1
+MODEL_EDGE_SINGLE_CTA = 1
+FLAG_NONFINITE = 1
+FLAG_TC_RANGE = 2
+TC_RANGE_LIMIT = 16384.0
 
 vp = C.c_void_p
 
@@ -37,6 +41,7 @@ class Model(C.Structure):
         ("film_wp_t", vp), ("film_time_table", vp),
         ("layers", LayerWeights * MAX_LAYERS),
         ("final_g", vp), ("final_b", vp), ("w_head", vp), ("b_head", vp), ("w_head_t", vp), ("w_lat", vp),
+        ("flags", C.c_int32),
     ]
 
 
@@ -58,7 +63,7 @@ class ForwardIO(C.Structure):
     _fields_ = [
         ("atom_types", vp), ("frac_coords", vp), ("lattices", vp), ("film_cond", vp),
         ("head_out", vp), ("lattice_out", vp), ("node_features", vp),
-        ("coords_only", C.c_int32), ("precision", C.c_int32),
+        ("coords_only", C.c_int32), ("precision", C.c_int32), ("flags", vp),
     ]
 
 
@@ -81,13 +86,15 @@ EXPORTS = {
     "cb2_abi_version": (C.c_int, []),
     "cb2_last_error": (C.c_char_p, []),
     "cb2_check_device": (C.c_int, [C.c_int]),
-    "cb2_workspace_bytes": (C.c_size_t, [C.POINTER(Batch), C.c_int]),
+    "cb2_workspace_bytes": (C.c_size_t, [C.POINTER(Model), C.POINTER(Batch), C.c_int]),
     "cb2_embed_nodes": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), vp, vp, vp]),
     "cb2_film_cond": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), vp, vp, vp, vp]),
     "cb2_linear_f32": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, vp]),
-    "cb2_linear_tc": (C.c_int, [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]),
-    "cb2_edge_layer": (C.c_int, [C.POINTER(Model), C.c_int32, C.POINTER(Batch), vp, vp, vp, C.c_int64, C.c_int32,
+    "cb2_linear_tc": (C.c_int, [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                vp, C.c_size_t, vp]),
+    "cb2_linear_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "cb2_edge_layer": (C.c_int, [C.POINTER(Model), C.c_int32, C.POINTER(Batch), vp, vp, vp, vp, C.c_int64, C.c_int32,
                                  vp, C.c_size_t, vp]),
     "cb2_decoder_forward": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), C.POINTER(ForwardIO), vp,
                                       C.c_size_t, vp]),
@@ -112,13 +119,15 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
+
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise Cb2Error(f"{LIB_PATH} is missing and there is no fallback path; run "
                            "`python -m chemeleon_b200.build`")
-        from . import build as _build
-
         _build.build()
+    elif build_if_missing and _build.have_nvcc() and _build.needs_build():
+        _build.build()          # csrc/*.cu edited since the library was built: never run stale kernels
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in EXPORTS.items():
         try:

@@ -24,6 +24,10 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True

@@ -30,7 +30,7 @@ int launch_validity(const int64_t *a, const float *x, const float *lat, const in
                     const int32_t *target, float max_len, float thr, int32_t *flags, float *min_dist,
                     float *max_abc, cudaStream_t st);
 int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_out, cudaStream_t st);
-int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
+int launch_lattice_ip(const float *lat, const cb2_model *m, float *cg, int B, int32_t *range_flags, cudaStream_t st);
 int launch_edge_embed(const float *x, const int32_t *ei, const int32_t *ej, float *emb, int64_t n_rows,
                       cudaStream_t st);
 int launch_segment_mean(const float *e, const int64_t *node_eoff, const int32_t *node_n, float *out,
@@ -46,20 +46,20 @@ int update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, c
 int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                       cudaStream_t st);
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
-                     int64_t ldc, int64_t M, int K, int silu, cudaStream_t st);
+                     int64_t ldc, int64_t M, int K, int silu, void *workspace, size_t workspace_bytes, cudaStream_t st);
 int debug_edge_timeline(long long *out96);
-int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P, __half *agg16,
-                  int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
+int tc_edge_layer(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P,
+                  const float *cg, __half *agg16, int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
 
-size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) {
+size_t carve_forward(Arena &a, const cb2_batch *b, int n_layers, int precision, ForwardWs &w) {
   const size_t VN = (size_t)b->n_variants * b->n_nodes;
   w = ForwardWs{};
   w.h = a.take<float>(VN * H);
-  w.y = a.take<float>(VN * H);
-  w.P = a.take<float>(VN * H2);
   w.hf = a.take<float>(VN * H);
-  w.cg = a.take<float>((size_t)b->n_graphs * H);
+  w.cg = a.take<float>((size_t)n_layers * b->n_graphs * H);
   if (precision == CB2_PRECISION_FP32) {
+    w.y = a.take<float>(VN * H);
+    w.P = a.take<float>(VN * H2);
     w.cat = a.take<float>(VN * H2);
     w.z1 = a.take<float>(VN * H);
     const size_t ec = (size_t)b->chunk_max_edges;
@@ -67,7 +67,9 @@ size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w) 
     w.a1 = a.take<float>(ec * H);
     w.e2 = a.take<float>(ec * H);
   } else {
+    // tensor-core path: the FiLM projection y never leaves TMEM and P is fp16
     const size_t VNp = (VN + 127) / 128 * 128;   // row-panel layout: whole panels of 128 rows
+    w.P = reinterpret_cast<float *>(a.take<__half>(VN * H2));
     w.h16 = a.take<__half>(VNp * H);
     w.cat16 = a.take<__half>(VNp * H2);
     w.z16 = a.take<__half>(VNp * H);
@@ -117,7 +119,7 @@ static int check_batch(const cb2_batch *b, int precision) {
 
 // ---- exact-mode edge model of one layer: emb -> GEMM1(+P gather, SiLU) -> GEMM2 -> segment mean ----
 static int f32_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const float *P,
-                          float *agg, int64_t ld_agg, ForwardWs &w, cudaStream_t st) {
+                          const float *cg, float *agg, int64_t ld_agg, ForwardWs &w, cudaStream_t st) {
   const int N = b->n_nodes, V = b->n_variants;
   for (int c = 0; c < b->n_chunks; c++) {
     const int nlo = b->host_chunk_node_lo[c], nhi = b->host_chunk_node_lo[c + 1];
@@ -129,6 +131,7 @@ static int f32_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const 
     for (int v = 0; v < V; v++) {
       GemmEpilogue e1p;
       e1p.P = P; e1p.ei = b->edge_i + e0; e1p.ej = b->edge_j + e0; e1p.prow_off = (int64_t)v * N;
+      e1p.ecg = cg; e1p.n2g = b->node2graph;
       e1p.silu = 1;
       CB2_TRY(launch_sgemm_nt(w.emb, DIS, L.w_fd, w.a1, H, rows, H, DIS, e1p, st));
       GemmEpilogue e2p;
@@ -145,6 +148,7 @@ static int f32_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_
                               cudaStream_t st) {
   const int N = b->n_nodes, B = b->n_graphs, V = b->n_variants;
   const int64_t VN = (int64_t)V * N;
+  CB2_TRY(launch_lattice_ip(io->lattices, m, w.cg, B, nullptr, st));      // all layers' lattice terms, one launch
   for (int li = 0; li < m->n_layers; li++) {
     const cb2_layer_weights &L = m->layers[li];
     if (io->film_cond != nullptr) {
@@ -154,13 +158,11 @@ static int f32_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_
     }
     CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
                               w.cat, H2, nullptr, 0, 0, N, B, V, st));
-    CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
     {
-      GemmEpilogue e;  // P = hn [W_hi;W_hj]^T, lattice term + b1 folded into the P_i half
-      e.gbias = w.cg; e.gidx = b->node2graph; e.gmod = N; e.gcols = H; e.gld = H;
+      GemmEpilogue e;  // P = hn [W_hi;W_hj]^T; the lattice term + b1 (cg) joins it per edge
       CB2_TRY(launch_sgemm_nt(w.cat, H2, L.w_hij, w.P, H2, VN, H2, H, e, st));
     }
-    CB2_TRY(f32_edge_layer(L, b, io->frac_coords, w.P, w.cat + H, H2, w, st));
+    CB2_TRY(f32_edge_layer(L, b, io->frac_coords, w.P, w.cg + (size_t)li * B * H, w.cat + H, H2, w, st));
     {
       GemmEpilogue e;
       e.bias = L.bn1; e.silu = 1;
@@ -237,12 +239,12 @@ int cb2_check_device(int device) {
   return CB2_OK;
 }
 
-size_t cb2_workspace_bytes(const cb2_batch *batch, int precision) {
-  if (!batch) return 0;
+size_t cb2_workspace_bytes(const cb2_model *m, const cb2_batch *batch, int precision) {
+  if (!batch || !m) return 0;
   Arena a(nullptr, 0, true);
   ForwardWs fw;
   StepWs sw;
-  carve_forward(a, batch, precision, fw);
+  carve_forward(a, batch, m->n_layers, precision, fw);
   carve_step(a, batch, sw);
   return a.off + 256;
 }
@@ -272,14 +274,21 @@ int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bia
   return launch_sgemm_nt(A, lda, W, C, ldc, M, N, K, e, (cudaStream_t)stream);
 }
 
+size_t cb2_linear_tc_workspace_bytes(int64_t M, int32_t K) {
+  if (M <= 0 || K <= 0) return 0;
+  return (size_t)((M + 127) / 128 * 128) * (size_t)K * sizeof(__half);
+}
+
 int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
-                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream) {
+                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *workspace, size_t workspace_bytes,
+                  void *stream) {
   if (!A16 || !Wt || !C) return fail(CB2_ERR_BAD_ARG, "linear_tc: null argument");
-  return tc_linear_simple(A16, lda, Wt, Nw, bias, C, ldc, M, K, silu, (cudaStream_t)stream);
+  return tc_linear_simple(A16, lda, Wt, Nw, bias, C, ldc, M, K, silu, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
 }
 
 int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
-                   const void *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   const void *P, const float *cg, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
                    size_t workspace_bytes, void *stream) {
   CB2_TRY(check_model(m));
   CB2_TRY(check_batch(b, precision));
@@ -289,12 +298,12 @@ int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const 
   if (precision == CB2_PRECISION_FP32) {
     Arena a(workspace, workspace_bytes, false);
     ForwardWs fw;
-    carve_forward(a, b, precision, fw);
+    carve_forward(a, b, m->n_layers, precision, fw);
     if (!workspace || !a.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
-    return f32_edge_layer(L, b, frac_coords, (const float *)P, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
+    return f32_edge_layer(L, b, frac_coords, (const float *)P, cg, (float *)agg, ld_agg, fw, (cudaStream_t)stream);
   }
   if (!L.w_fd_t || !L.w2_t) return fail(CB2_ERR_BAD_ARG, "edge_layer: fp16 operand images missing");
-  return tc_edge_layer(L, b, frac_coords, (const __half *)P, (__half *)agg, ld_agg, 0, 0, (cudaStream_t)stream);
+  return tc_edge_layer(m, L, b, frac_coords, (const __half *)P, cg, (__half *)agg, ld_agg, 0, 0, (cudaStream_t)stream);
 }
 
 int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, void *workspace,
@@ -306,7 +315,7 @@ int cb2_decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_forwar
     return fail(CB2_ERR_BAD_ARG, "forward: null state/output pointer");
   Arena a(workspace, workspace_bytes, false);
   ForwardWs fw;
-  carve_forward(a, b, io->precision, fw);
+  carve_forward(a, b, m->n_layers, io->precision, fw);
   if (!workspace || !a.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
   return decoder_forward(m, b, io, fw, (cudaStream_t)stream);
 }
@@ -332,7 +341,7 @@ int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const
   Arena ar(workspace, workspace_bytes, false);
   ForwardWs fw;
   StepWs sw;
-  carve_forward(ar, b, a->precision, fw);
+  carve_forward(ar, b, m->n_layers, a->precision, fw);
   carve_step(ar, b, sw);
   if (!workspace || !ar.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
   CB2_TRY(launch_film_cond(m->film_time_table, a->text_part, s->t_dev, sw.film_cond,
@@ -347,6 +356,7 @@ int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const
   io.node_features = nullptr;
   io.coords_only = 0;
   io.precision = a->precision;
+  io.flags = s->flags;
   CB2_TRY(decoder_forward(m, b, &io, fw, st));                        // predictor (cond | null)
   CB2_TRY(update_predictor(b, s, a, sw.head_out, sw.lat_out, st));
   io.coords_only = 1;

@@ -66,10 +66,11 @@ struct ForwardWs {
   float *h;       // [VN,512] residual stream
   float *y;       // [VN,512] FiLM projection / scratch
   float *cat;     // [VN,1024] cols 0:512 = LN(h) (hn), 512:1024 = aggregated edge features
-  float *P;       // [VN,1024] hoisted edge-MLP terms: P_i (+ lattice term + b1) | P_j
+  float *P;       // [VN,1024] hoisted edge-MLP terms P_i | P_j = hn [W_hi;W_hj]^T (fp16 on the tensor-core path);
+                  //           the per-crystal term cg stays separate, in fp32
   float *z1;      // [VN,512] node-MLP hidden
   float *hf;      // [VN,512] final-LN features (when the caller does not want them)
-  float *cg;      // [B,512]  W_ip vec(L L^T) + b1
+  float *cg;      // [n_layers,B,512]  W_ip vec(L L^T) + b1 of every layer (one launch per forward)
   float *emb;     // [Ec,768] exact path: sinusoid embedding of an edge chunk
   float *a1;      // [Ec,512]
   float *e2;      // [Ec,512]
@@ -77,7 +78,6 @@ struct ForwardWs {
   __half *h16;    // [VN,512]
   __half *cat16;  // [VN,1024]
   __half *z16;    // [VN,512]
-  float *sincos;  // [N,768] per-node sin/cos tables (unused in v1)
 };
 
 // Buffers the sampler step adds on top of ForwardWs.
@@ -87,7 +87,7 @@ struct StepWs {
   float *lat_out;    // [VB,9]
 };
 
-size_t carve_forward(Arena &a, const cb2_batch *b, int precision, ForwardWs &w);
+size_t carve_forward(Arena &a, const cb2_batch *b, int n_layers, int precision, ForwardWs &w);
 size_t carve_step(Arena &a, const cb2_batch *b, StepWs &w);
 
 // ---- launchers implemented across the .cu files ------------------------------
@@ -102,6 +102,9 @@ struct GemmEpilogue {
   const int32_t *ei = nullptr;
   const int32_t *ej = nullptr;
   int64_t prow_off = 0;
+  // ... + cg[n2g[ei[r]] * 512 + c]: per-crystal lattice term of the edge MLP (only with P)
+  const float *ecg = nullptr;
+  const int32_t *n2g = nullptr;
   int silu = 0;
   const float *residual = nullptr;   // [M, ldr] added after the activation
   int64_t ldr = 0;

@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(256) k_sgemm_nt(const float *__restrict__ A, i
     if (r >= M) continue;
     const float *gb = nullptr;
     if (epi.gbias != nullptr) gb = epi.gbias + (int64_t)epi.gidx[r % epi.gmod] * epi.gld;
-    const float *pi = nullptr, *pj = nullptr;
+    const float *pi = nullptr, *pj = nullptr, *ecg = nullptr;
     if (epi.P != nullptr) {
-      pi = epi.P + (epi.prow_off + epi.ei[r]) * H2;
+      const int ni = epi.ei[r];
+      pi = epi.P + (epi.prow_off + ni) * H2;
       pj = epi.P + (epi.prow_off + epi.ej[r]) * H2 + H;
+      if (epi.ecg != nullptr) ecg = epi.ecg + (int64_t)epi.n2g[ni] * H;
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) k_sgemm_nt(const float *__restrict__ A, i
       if (epi.bias != nullptr) v += epi.bias[c];
       if (gb != nullptr && c < epi.gcols) v += gb[c];
       if (pi != nullptr) v += pi[c] + pj[c];
+      if (ecg != nullptr) v += ecg[c];
       if (epi.silu) v = silu_exact(v);
       if (epi.residual != nullptr) v += epi.residual[r * epi.ldr + c];
       acc[i][j] = v;
@@ -333,9 +336,15 @@ int launch_layernorm(const float *x, const float *g, const float *b, float *out,
 // lattice term of the edge MLP, once per crystal:
 //   cg[g] = W_ip vec(L L^T) + b1                       (cspnet.py:143-149, hoisted)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_lattice_ip(const float *__restrict__ lat, const float *__restrict__ w_ip,
-                                                    const float *__restrict__ b1, float *__restrict__ cg) {
-  int g = blockIdx.x;
+struct LatticeIpLayers {
+  const float *w_ip[CB2_MAX_LAYERS];
+  const float *b1[CB2_MAX_LAYERS];
+};
+
+// grid = (B, n_layers): one launch per forward covers every layer's term, cg[l][g][:]
+__global__ void __launch_bounds__(512) k_lattice_ip(const float *__restrict__ lat, LatticeIpLayers lw,
+                                                    float *__restrict__ cg, int B, int32_t *__restrict__ range_flags) {
+  const int g = blockIdx.x, li = blockIdx.y;
   __shared__ float ip[9];
   if (threadIdx.x < 9) {
     int a = threadIdx.x / 3, b = threadIdx.x % 3;
@@ -343,16 +352,25 @@ __global__ void __launch_bounds__(512) k_lattice_ip(const float *__restrict__ la
     ip[threadIdx.x] = L[a * 3 + 0] * L[b * 3 + 0] + L[a * 3 + 1] * L[b * 3 + 1] + L[a * 3 + 2] * L[b * 3 + 2];
   }
   __syncthreads();
-  int c = threadIdx.x;
-  float s = b1[c];
+  const int c = threadIdx.x;
+  const float *w_ip = lw.w_ip[li];
+  float s = lw.b1[li][c];
 #pragma unroll
   for (int m = 0; m < 9; m++) s = fmaf(w_ip[c * 9 + m], ip[m], s);
-  cg[(int64_t)g * H + c] = s;
+  cg[((int64_t)li * B + g) * H + c] = s;
+  // tensor-core mode: outside this range the fp16 GEMM2 operand saturates -- tell the caller
+  if (range_flags != nullptr && !(fabsf(s) <= CB2_TC_RANGE_LIMIT)) atomicOr(range_flags + g, CB2_FLAG_TC_RANGE);
 }
 
-int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st) {
+// cg: [n_layers, B, 512]
+int launch_lattice_ip(const float *lat, const cb2_model *m, float *cg, int B, int32_t *range_flags, cudaStream_t st) {
   if (B == 0) return CB2_OK;
-  k_lattice_ip<<<B, 512, 0, st>>>(lat, w_ip, b1, cg);
+  LatticeIpLayers lw;
+  for (int li = 0; li < m->n_layers; li++) {
+    lw.w_ip[li] = m->layers[li].w_ip;
+    lw.b1[li] = m->layers[li].b1;
+  }
+  k_lattice_ip<<<dim3((unsigned)B, (unsigned)m->n_layers), 512, 0, st>>>(lat, lw, cg, B, range_flags);
   CB2_LAUNCH_OK("k_lattice_ip");
   return CB2_OK;
 }

@@ -240,15 +240,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tc_linear(TcLinearArgs g) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-static int g_num_sms = 0;
-
-static int num_sms(int *out) {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    CB2_CUDA_OK(cudaGetDevice(&dev));
-    CB2_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  *out = g_num_sms;
+// SM count of the CURRENT device (queried per call: the library keeps no per-process device state,
+// so engines on several GPUs of one process each get their own answer)
+int num_sms(int *out) {
+  int dev = 0;
+  CB2_CUDA_OK(cudaGetDevice(&dev));
+  CB2_CUDA_OK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
   return CB2_OK;
 }
 
@@ -257,11 +254,8 @@ int launch_tc_linear(const TcLinearArgs &a, cudaStream_t st) {
   if (a.K % TL_KC != 0 || a.K <= 0 || a.Nw % TL_NB != 0 || a.a_kt % 8 != 0 || (a.a_wrap == 0 && a.K > a.a_kt) ||
       a.a_wrap * TL_KC > a.a_kt || (a.n_store % 64) != 0)
     return fail(CB2_ERR_BAD_ARG, "tc_linear: K%64, N%256, a_kt%8, n_store%64 must be 0 and K <= a_kt");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
-    attr_set = true;
-  }
+  // per-device function attribute: set on every launch (cheap, legal during stream capture)
+  CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM));
   int sms = 0;
   CB2_TRY(num_sms(&sms));
   const int64_t n_tiles = ((a.M + TL_BM - 1) / TL_BM) * (a.Nw / TL_NB);
@@ -311,35 +305,32 @@ static int launch_to_panels(const T *x, int64_t ldx, __half *y, int64_t M, int K
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
-int launch_lattice_ip(const float *lat, const float *w_ip, const float *b1, float *cg, int B, cudaStream_t st);
+int launch_lattice_ip(const float *lat, const cb2_model *m, float *cg, int B, int32_t *range_flags, cudaStream_t st);
 int launch_tc_film(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *film_cond,
                    const __half *h16, float *h, __half *cat16, int n_sm, cudaStream_t st);
 
-// C-ABI unit entry: row-major fp16 A; the row-panel copy the kernel reads is made here.
+// C-ABI unit entry: row-major fp16 A; the row-panel copy the kernel reads is made in the caller's workspace.
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
-                     int64_t ldc, int64_t M, int K, int silu, cudaStream_t st) {
+                     int64_t ldc, int64_t M, int K, int silu, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   if (M == 0) return CB2_OK;
   if (K % TL_KC != 0 || lda % 8 != 0) return fail(CB2_ERR_BAD_ARG, "linear_tc: K%64 and lda%8 must be 0");
-  __half *panels = nullptr;
   const int64_t Mp = (M + 127) / 128 * 128;
-  CB2_CUDA_OK(cudaMallocAsync((void **)&panels, (size_t)Mp * K * sizeof(__half), st));
-  int rc = launch_to_panels<__half>((const __half *)A16, lda, panels, M, K, K, 0, st);
-  if (rc == CB2_OK) {
-    TcLinearArgs a{};
-    a.A = panels; a.a_kt = K; a.M = M; a.K = K; a.Wt = (const __half *)Wt; a.Nw = Nw;
-    a.C = C; a.ldc = ldc; a.bias = bias; a.silu = silu;
-    rc = launch_tc_linear(a, st);
-  }
-  CB2_CUDA_OK(cudaFreeAsync(panels, st));
-  return rc;
+  if (!workspace || workspace_bytes < (size_t)Mp * K * sizeof(__half))
+    return fail(CB2_ERR_WORKSPACE, "linear_tc: workspace too small: call cb2_linear_tc_workspace_bytes()");
+  __half *panels = reinterpret_cast<__half *>(workspace);
+  CB2_TRY(launch_to_panels<__half>((const __half *)A16, lda, panels, M, K, K, 0, st));
+  TcLinearArgs a{};
+  a.A = panels; a.a_kt = K; a.M = M; a.K = K; a.Wt = (const __half *)Wt; a.Nw = Nw;
+  a.C = C; a.ldc = ldc; a.bias = bias; a.silu = silu;
+  return launch_tc_linear(a, st);
 }
 
-int tc_edge_layer(const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P, __half *agg16,
-                  int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st) {
+int tc_edge_layer(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P,
+                  const float *cg, __half *agg16, int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st) {
   int sms = 0;
   CB2_TRY(num_sms(&sms));
   TcEdgeArgs e{};
-  e.P = P; e.x = x; e.row_i = b->tile_row_i; e.row_j = b->tile_row_j; e.seg_n = b->tile_seg_n;
+  e.P = P; e.x = x; e.cg = cg; e.node2graph = b->node2graph; e.single_cta = (m->flags & CB2_MODEL_EDGE_SINGLE_CTA) != 0; e.row_i = b->tile_row_i; e.row_j = b->tile_row_j; e.seg_n = b->tile_seg_n;
   e.w_fd_t = (const __half *)L.w_fd_t; e.w2_t = (const __half *)L.w2_t; e.b2 = L.b2;
   e.agg16 = agg16; e.ld_agg = ld_agg; e.agg_col = agg_col; e.agg_kt = agg_kt; e.N = b->n_nodes; e.V = b->n_variants;
   e.n_tiles = b->n_tiles;
@@ -366,39 +357,28 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
   const int64_t VN = (int64_t)V * N;
   if (!m->film_wp_t) return fail(CB2_ERR_BAD_ARG, "tensor-core path needs the fp16 operand images (pack with tensor_core=True)");
   if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
-  static int fused_film = -1;       // CB2_FILM_FUSED=0: separate FiLM GEMM + k_film_apply (A-B knob)
-  if (fused_film < 0) {
-    const char *e = getenv("CB2_FILM_FUSED");
-    fused_film = (e && atoi(e) == 0) ? 0 : 1;
-  }
   int sms = 0;
   CB2_TRY(num_sms(&sms));
+  CB2_TRY(launch_lattice_ip(io->lattices, m, w.cg, B, io->flags, st));      // all layers' lattice terms, one launch
   for (int li = 0; li < m->n_layers; li++) {
     const cb2_layer_weights &L = m->layers[li];
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
-    if (io->film_cond != nullptr && fused_film) {
+    if (io->film_cond != nullptr) {
       // FiLM projection + LN + FiLM + SiLU + residual + layer LN in one kernel (y stays in TMEM)
       CB2_TRY(launch_tc_film(m, L, b, io->film_cond, w.h16, w.h, w.cat16, sms, st));
     } else {
-      if (io->film_cond != nullptr) {
-        TcLinearArgs a{};
-        a.A = w.h16; a.a_kt = H; a.M = VN; a.K = H; a.Wt = (const __half *)m->film_wp_t; a.Nw = H;
-        a.C = w.y; a.ldc = H; a.bias = m->film_bp;
-        CB2_TRY(launch_tc_linear(a, st));
-      }
-      CB2_TRY(launch_film_apply(w.y, w.h, io->film_cond, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
+      CB2_TRY(launch_film_apply(nullptr, w.h, nullptr, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
                                 nullptr, 0, w.cat16, 0, H2, N, B, V, st));
     }
-    CB2_TRY(launch_lattice_ip(io->lattices, L.w_ip, L.b1, w.cg, B, st));
     {
-      TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T  (+ lattice term + b1 on the P_i half)
+      TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T in fp16; the per-crystal lattice term stays in fp32 (cg)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
-      a.C16r = reinterpret_cast<__half *>(w.P); a.ldc16r = H2;   // fp16: the edge kernel gathers half the bytes
-      a.gbias = w.cg; a.gidx = b->node2graph; a.gmod = N; a.gcols = H; a.gld = H;
+      a.C16r = reinterpret_cast<__half *>(w.P); a.ldc16r = H2;
       CB2_TRY(launch_tc_linear(a, st));
     }
-    CB2_TRY(tc_edge_layer(L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P), w.cat16, 0, H, H2, st));
+    CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P),
+                          w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
     {
       TcLinearArgs a{};   // z = SiLU([hn|agg] Wn1^T + bn1)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;

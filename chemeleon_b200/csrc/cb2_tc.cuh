@@ -34,7 +34,10 @@ __device__ __forceinline__ uint32_t silu2_half(float a, float b) {
 }
 
 struct TcEdgeArgs {
-  const __half *P;         // [V*N,1024] fp16 row-major hoisted terms (P_i + lattice term + b1 | P_j)
+  const __half *P;         // [V*N,1024] fp16 row-major hoisted terms (P_i | P_j)
+  const float *cg;         // [B,512] fp32 per-crystal term W_ip vec(L L^T) + b1 (NULL = 0); added in E1, never rounded to fp16
+  const int32_t *node2graph;
+  int single_cta;          // V == 2: force the one-CTA kernel (cb2_model.flags & CB2_MODEL_EDGE_SINGLE_CTA)
   const float *x;          // [N,3]
   const int32_t *row_i;    // [n_tiles*128] node i of the tile's edge row, -1 = padding
   const int32_t *row_j;

@@ -143,8 +143,15 @@ __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, c
 // structure is compile-time, each thread loads P_i once per segment and the N rows of P_j once
 // per crystal (they repeat for every segment of the same crystal).  N == 0: generic version, two
 // gathers per edge.
+// The per-crystal lattice term cg[g][c] (fp32, O(10..100) for Angstrom-scale cells) is added here in
+// fp32 -- it is never folded into the fp16 P rows, whose O(1) node signal it would swamp.
+struct E1Cg { const float *cgc; const int32_t *n2g; uint32_t vbase; };   // cgc = cg + channel (NULL: no term)
+__device__ __forceinline__ float e1_cg(const E1Cg &k, uint32_t oi) {
+  return k.cgc ? __ldg(k.cgc + (size_t)__ldg(k.n2g + ((oi >> 10) - k.vbase)) * H) : 0.f;
+}
+
 template <int N>
-__device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, const uint32_t *t_oi, const uint32_t *t_oj,
+__device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, E1Cg cgk, const uint32_t *t_oi, const uint32_t *t_oj,
                                      uint8_t *a1_dst, uint32_t acc1_full, uint32_t parity) {
   if constexpr (N == 0) {
     const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
@@ -162,7 +169,8 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, const uin
         const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
         const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) pv[j4 * 4 + k] = __half2float(Pc[ois[k] == TE_PAD ? 0u : ois[k]]) + __half2float(Pc[ojs[k]]);
+        for (int k = 0; k < 4; k++)
+          pv[j4 * 4 + k] = ois[k] == TE_PAD ? 0.f : __half2float(Pc[ois[k]]) + e1_cg(cgk, ois[k]) + __half2float(Pc[ojs[k]]);
       }
       tmem_ld_wait();
 #pragma unroll
@@ -181,7 +189,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, const uin
 #pragma unroll
     for (int sgm = 0; sgm < S; sgm++) {
       const uint32_t oi = t_oi[sgm * N];
-      piv[sgm] = __half2float(Pc[oi == TE_PAD ? 0u : oi]);
+      piv[sgm] = oi == TE_PAD ? 0.f : __half2float(Pc[oi]) + e1_cg(cgk, oi);
     }
     float pj[N];
     uint32_t cur = t_oj[0];
@@ -227,11 +235,11 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, const uin
   }
 }
 
-__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half *Pc, const uint32_t *t_oi,
+__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half *Pc, E1Cg cgk, const uint32_t *t_oi,
                                             const uint32_t *t_oj, uint8_t *a1_dst, uint32_t acc1_full,
                                             uint32_t parity) {
   switch (n) {
-#define CB2_E1_CASE(N) case N: e1_unit<N>(taddr, Pc, t_oi, t_oj, a1_dst, acc1_full, parity); break;
+#define CB2_E1_CASE(N) case N: e1_unit<N>(taddr, Pc, cgk, t_oi, t_oj, a1_dst, acc1_full, parity); break;
     CB2_E1_CASE(4) CB2_E1_CASE(5) CB2_E1_CASE(6) CB2_E1_CASE(7)
     CB2_E1_CASE(8) CB2_E1_CASE(9) CB2_E1_CASE(10) CB2_E1_CASE(11) CB2_E1_CASE(12) CB2_E1_CASE(13)
     CB2_E1_CASE(14) CB2_E1_CASE(15) CB2_E1_CASE(16) CB2_E1_CASE(17) CB2_E1_CASE(18) CB2_E1_CASE(19)
@@ -240,7 +248,7 @@ __device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half 
     CB2_E1_CASE(32) CB2_E1_CASE(33) CB2_E1_CASE(34) CB2_E1_CASE(35) CB2_E1_CASE(36) CB2_E1_CASE(37)
     CB2_E1_CASE(38) CB2_E1_CASE(39) CB2_E1_CASE(40)
 #undef CB2_E1_CASE
-    default: e1_unit<0>(taddr, Pc, t_oi, t_oj, a1_dst, acc1_full, parity); break;
+    default: e1_unit<0>(taddr, Pc, cgk, t_oi, t_oj, a1_dst, acc1_full, parity); break;
   }
 }
 
@@ -556,7 +564,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       if (has_next) publish_rows(next, buf ^ 1, dlt_next);
       // ---- E1: a1 = SiLU(U + P_i + P_j), thread = channel, MN-major fp16 operand of GEMM2 ----
       if (tid == 0) TE_STAMP(8);
-      e1_dispatch(n, taddr, Pc, t_oi, t_oi + 128, a1_dst, acc1_full, it & 1);
+      const E1Cg cgk{g.cg ? g.cg + c : nullptr, g.node2graph, (uint32_t)(item / g.n_tiles) * (uint32_t)g.N};
+      e1_dispatch(n, taddr, Pc, cgk, t_oi, t_oi + 128, a1_dst, acc1_full, it & 1);
       if (tid == 0) TE_STAMP(9);
       {  // pre-load the unit with b2: every GEMM2 MMA accumulates, so the issuers need no ordering
         uint32_t bv[32];
@@ -592,353 +601,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
   if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
-// =============================================================================================
-// k_tc_edge_pair: the same layer for the two classifier-free-guidance variants at once, on a
-// CTA PAIR (cluster of 2).  The sinusoid term W_fd emb(x_j - x_i) does not depend on the variant
-// (cond and null share the state), so GEMM1 -- 60 % of the edge FLOPs -- is computed once per
-// edge instead of once per (edge, variant):
-//
-//   CTA r, GEMM1: U = W_fd[256 r : 256 r + 256] emb^T         two units X0, X1 (TMEM columns 0:256)
-//   E1 (group = (unit m', variant v)): a1_v[256 r + 128 m' ..] = SiLU(U + P^v_i + P^v_j), written
-//       into the shared memory of CTA v -- its own (v == r) or the peer's, through the
-//       distributed-shared-memory window (generic stores to the mapped address)
-//   CTA r, GEMM2 + E2 for variant r: all 512 output channels, units O0..O3 (O0, O1 re-use X0, X1)
-//
-// Per tile and CTA: 96 + 128 MMAs instead of 192 + 128, 896 KB of weights instead of 1280 KB.
-// a1 K stage k lives in slot (k - 2 r) & 3 of the a1 region: the locally produced stages in the
-// lower 64 KB (which double as the embedding ring, dead once GEMM1 has completed), the peer's in
-// the upper 64 KB (which double as the two extra GEMM1 weight stages) -- acc1_full is therefore a
-// multicast commit: it completes when BOTH CTAs have finished GEMM1 of the tile (and hence GEMM2
-// of the previous one), which is exactly when either CTA may write into the other's upper half.
-//   barriers (per CTA): acc1_full, g2_done (2 x 3 multicast commits), a1_ready (256 local + 256 remote arrivals),
-//   out_ready (512: every E1 thread has read its X unit and O0/O1 hold b2;  + 256: O2/O3 hold b2)
-// =============================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TE_THREADS, 1) k_tc_edge_pair(TcEdgeArgs g) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + TE_BAR_OFF;
-  auto a_full = [&](int s) { return bars + 8 * s; };            // 8
-  auto a_empty = [&](int s) { return bars + 64 + 8 * s; };      // 8
-  auto w_full = [&](int s) { return bars + 128 + 8 * s; };      // 5
-  auto w_empty = [&](int s) { return bars + 168 + 8 * s; };     // 5
-  const uint32_t acc1_full = bars + 208, a1_ready = bars + 216;
-  auto acc2_full = [&](int u) { return bars + 224 + 8 * u; };
-  auto acc_init = [&](int u) { return bars + 256 + 8 * u; };    // 2 used
-  const uint32_t out_ready = bars + 272, g2_done = bars + 280;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TE_BAR_OFF + 288);
-  auto w_addr = [&](int s) {
-    return s < TE_WSTAGES ? sbase + TE_W_OFF + s * TE_W_BYTES : sbase + TE_WEXTRA_OFF + (s - TE_WSTAGES) * TE_W_BYTES;
-  };
-  uint32_t *tab = reinterpret_cast<uint32_t *>(smem + TE_TAB_OFF);   // [buf][0: off_i, 1: off_j][128], variant 0 offsets
-
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
-  const int cl = blockIdx.x >> 1, n_cl = gridDim.x >> 1;           // cluster id / number of clusters
-  if (tid == 0) {
-    for (int s = 0; s < TE_ASLOTS; s++) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < TE_WSTAGES + TE_WEXTRA; s++) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    mbar_init(acc1_full, 2 * TE_NISSUE);
-    mbar_init(g2_done, 2 * TE_NISSUE);
-    mbar_init(a1_ready, TE_WORKERS);
-    mbar_init(out_ready, TE_WORKERS + 256);
-    for (int u = 0; u < 4; u++) mbar_init(acc2_full(u), TE_NISSUE);
-    for (int u = 0; u < 2; u++) mbar_init(acc_init(u), 128);
-    fence_barrier_init();
-  }
-  if (warp == 16) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();               // the peer's barriers are initialised before anybody arrives on them
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const int n_items = g.n_tiles;     // one item = one tile, both variants
-
-  if (warp == 16 + TE_NISSUE) {
-    // ------------------------------ weight loader ------------------------------
-    if (lane == 0) {
-      uint32_t use[TE_WSTAGES + TE_WEXTRA] = {0, 0, 0, 0, 0};
-      uint32_t it = 0;
-      for (int item = cl; item < n_items; item += n_cl, it++) {
-        bool a1_dead = (it == 0);
-#pragma unroll
-        for (int sg = 0; sg < 12; sg++) {          // GEMM1: K = 64 per stage, my 256 channels: [8 k8][256][16 B]
-          const int st = sg % (TE_WSTAGES + TE_WEXTRA);
-          if (st >= TE_WSTAGES && !a1_dead) {       // the extra stages alias the peer-written a1 slots of the previous tile
-            mbar_wait_spin_cluster(g2_done, (it - 1) & 1);
-            a1_dead = true;
-          }
-          MBAR_WAIT_CRIT(w_empty(st), (use[st] & 1) ^ 1);
-          mbar_arrive_expect_tx(w_full(st), TE_W_BYTES);
-#pragma unroll
-          for (int k8 = 0; k8 < 8; k8++)
-            bulk_g2s(w_addr(st) + k8 * 4096, g.w_fd_t + ((int64_t)(sg * 8 + k8) * H + 256 * rank) * 8, 4096, w_full(st));
-          use[st]++;
-        }
-#pragma unroll
-        for (int c2 = 0; c2 < 16; c2++) {          // GEMM2: ring R1 only, W2 block (u, k) = c2
-          const int st = c2 % TE_WSTAGES;
-          MBAR_WAIT_CRIT(w_empty(st), (use[st] & 1) ^ 1);
-          mbar_arrive_expect_tx(w_full(st), TE_W_BYTES);
-          bulk_g2s(w_addr(st), g.w2_t + (int64_t)c2 * (TE_W_BYTES / 2), TE_W_BYTES, w_full(st));
-          use[st]++;
-        }
-      }
-    }
-  } else if (warp >= 16 && warp < 16 + TE_NISSUE) {
-    // ------------------------------ MMA issuers ------------------------------
-    if (lane == 0) {
-      const int ii = warp - 16;
-      constexpr uint32_t idesc_kk = idesc_f16_f32(128, 128);
-      constexpr uint32_t idesc_kmn = idesc_b_mn(idesc_f16_f32(128, 128));
-      constexpr int NS = TE_WSTAGES + TE_WEXTRA;
-      uint32_t it = 0;
-      const uint64_t d_lbo2k = smem_desc_kmajor(sbase, 2048, 128);   // emb slots, a1, W2 stages
-      const uint64_t d_lbo4k = smem_desc_kmajor(sbase, 4096, 128);   // W_fd half stages (256 channels)
-      auto w_off = [](int st) { return st < TE_WSTAGES ? TE_W_OFF + st * TE_W_BYTES : TE_WEXTRA_OFF + (st - TE_WSTAGES) * TE_W_BYTES; };
-      // uses of weight stage st per item: GEMM1 stage sg uses sg % 5 (12 stages), GEMM2 block c2 uses c2 % 3
-      auto g1_uses = [](int st) { return st < 2 ? 3u : 2u; };
-      auto uses_per_item = [](int st) { return st == 0 ? 9u : st == 1 ? 8u : st == 2 ? 7u : 2u; };
-      for (int item = cl; item < n_items; item += n_cl, it++) {
-        if (ii == 0) TE_STAMP(0);
-        MBAR_WAIT_CRIT(acc_init(0), it & 1);       // X0, X1 are clear
-        MBAR_WAIT_CRIT(acc_init(1), it & 1);
-        tc_fence_after_sync();
-        if (ii == 0) TE_STAMP(1);
-#pragma unroll
-        for (int sg = 0; sg < 12; sg++) {
-          // The two embedding slots of stage sg come round again at stage sg + 4: both uses must be
-          // waited for by the SAME thread, in order -- a thread two phases ahead of an mbarrier sees
-          // the parity it waits for as already completed.  (The weight ring allows 10 chunks of
-          // run-ahead here, more than the 8-chunk period of the slots.)
-          if ((sg & 3) % TE_NISSUE != ii) continue;
-          const int ws = sg % NS;
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int kc = 2 * sg + h, as = (kc & 3) + 4 * ((kc >> 2) & 1);
-            MBAR_WAIT_CRIT(a_full(as), (it * 3 + (kc >> 3)) & 1);
-          }
-          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + sg / NS) & 1);
-          fence_proxy_async_all();
-          tc_fence_after_sync();
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int kc = 2 * sg + (j >> 1), as = (kc & 3) + 4 * ((kc >> 2) & 1);
-            const uint64_t bd = d_lbo2k + (uint64_t)((as * TE_A_BYTES + 2 * (j & 1) * 2048) >> 4);
-#pragma unroll
-            for (int m = 0; m < 2; m++) {
-              const uint64_t ad = d_lbo4k + (uint64_t)((w_off(ws) + 2 * j * 4096 + m * 2048) >> 4);
-              umma_f16(tmem + m * 128, ad, bd, idesc_kk, 1u);
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int kc = 2 * sg + h, as = (kc & 3) + 4 * ((kc >> 2) & 1);
-            umma_commit(a_empty(as));
-          }
-          umma_commit(w_empty(ws));
-        }
-        umma_commit_multicast(acc1_full, (uint16_t)3);   // both CTAs learn that this CTA's GEMM1 has completed
-        if (ii == 0) TE_STAMP(2);
-        // GEMM2 (variant = rank): O_u += W2[u][k] a1[slot(k)]^T, unit after unit
-        mbar_wait_spin_cluster(a1_ready, it & 1);
-        MBAR_WAIT_CRIT(out_ready, it & 1);
-        fence_proxy_async_all();
-        tc_fence_after_sync();
-        if (ii == 0) TE_STAMP(3);
-#pragma unroll
-        for (int c2 = 0; c2 < 16; c2++) {
-          if (c2 % TE_NISSUE != ii) continue;
-          const int u = c2 / 4, kc = c2 % 4, ws = c2 % TE_WSTAGES;
-          const int slot = (kc - 2 * (int)rank) & 3;
-          MBAR_WAIT_CRIT(w_full(ws), (it * uses_per_item(ws) + g1_uses(ws) + c2 / TE_WSTAGES) & 1);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const uint64_t ad = d_lbo2k + (uint64_t)((w_off(ws) + 2 * j * 2048) >> 4);
-            const uint64_t bd = d_lbo2k + (uint64_t)(((slot * 16 + 2 * j) * 2048) >> 4);
-            umma_f16(tmem + u * 128, ad, bd, idesc_kmn, 1u);
-          }
-          umma_commit(w_empty(ws));
-          if (c2 + TE_NISSUE >= (u + 1) * 4) {
-            umma_commit(acc2_full(u));
-            if (c2 == (u + 1) * 4 - 1) TE_STAMP(4 + u);
-          }
-        }
-        umma_commit_multicast(g2_done, (uint16_t)3);   // both CTAs: this CTA no longer reads its a1 / embedding region
-      }
-    }
-  } else {
-    // ------------------------------ workers (512 threads) ------------------------------
-    const int q = warp % 4, u4 = warp / 4;       // TMEM lane quarter; embedding group / E2 unit / E1 (unit, variant)
-    const int r = q * 32 + lane;                 // edge row owned while producing the embedding
-    const int e1_m = u4 >> 1, e1_v = u4 & 1;     // E1: GEMM1 unit and variant of this group
-    const uint32_t taddr_x = tmem + ((uint32_t)(q * 32) << 16) + e1_m * 128;
-    const uint32_t taddr_o = tmem + ((uint32_t)(q * 32) << 16) + u4 * 128;
-    const int c_in = q * 32 + lane;                                  // channel within a 128-channel unit
-    const __half *Pc = g.P + (size_t)e1_v * (size_t)g.N * H2 + 256 * rank + e1_m * 128 + c_in;
-    const float bias_o = __ldg(g.b2 + u4 * 128 + c_in);              // b2 of the O unit this thread handles in E2
-    const float bias_x = __ldg(g.b2 + e1_m * 128 + c_in);            // b2 of O_{m'} (pre-loaded over X_{m'})
-    const int oc = g.agg_col + u4 * 128 + c_in;
-    __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
-    const AggStride agg_ld = g.agg_kt > 0 ? AggStride{(int64_t)128 * g.agg_kt, 8, rank * (uint32_t)g.N}
-                                          : AggStride{(int64_t)128 * g.ld_agg, (int)g.ld_agg, rank * (uint32_t)g.N};
-    // a1 destination: K stage 2 rank + m' of variant v lives in CTA v, slot m' (own) or 2 + m' (peer's)
-    const int a1_slot = (e1_v == (int)rank) ? e1_m : 2 + e1_m;
-    uint8_t *a1_local = smem + (size_t)a1_slot * 32768 + (size_t)(c_in / 8) * 2048 + (c_in % 8) * 16;
-    uint8_t *a1_dst = a1_local;
-    uint32_t a1_ready_dst = a1_ready;
-    if (e1_v != (int)rank) {
-      a1_dst = static_cast<uint8_t *>(__cluster_map_shared_rank(a1_local, peer));
-      a1_ready_dst = mapa_shared(a1_ready, peer);
-    }
-
-    int ri_p = -1, rj_p = 0;
-    auto fetch_rows = [&](int item) {
-      ri_p = g.row_i[(int64_t)item * 128 + r];
-      rj_p = g.row_j[(int64_t)item * 128 + r];
-    };
-    auto publish_rows = [&](int buf, float (&dl)[3]) {
-      dl[0] = dl[1] = dl[2] = 0.f;
-      if (ri_p >= 0) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) dl[d] = g.x[(int64_t)rj_p * 3 + d] - g.x[(int64_t)ri_p * 3 + d];
-      }
-      if (u4 == 0) {
-        uint32_t oi = TE_PAD, oj = (uint32_t)H;
-        if (ri_p >= 0) {
-          oi = (uint32_t)ri_p * (uint32_t)H2;
-          oj = (uint32_t)rj_p * (uint32_t)H2 + (uint32_t)H;
-        }
-        tab[buf * 256 + r] = oi;
-        tab[buf * 256 + 128 + r] = oj;
-      }
-    };
-    auto prefetch_rows = [&](int buf) {            // both variants' rows of P towards L2
-      const int e = (warp * 32 + lane) >> 2, sel = lane & 3;
-      const uint32_t o = tab[buf * 256 + ((sel & 1) ? 128 : 0) + e];
-      if (o != TE_PAD) {
-        const char *pp = reinterpret_cast<const char *>(g.P + (size_t)(sel >> 1) * (size_t)g.N * H2 + o);
-#pragma unroll
-        for (int l = 0; l < 8; l++) prefetch_l2(pp + l * 128);
-      }
-    };
-    auto fill_unit = [&](uint32_t ta, int c0, int ncol, uint32_t val) {   // tcgen05.st of a constant
-      uint32_t z[32];
-#pragma unroll
-      for (int j = 0; j < 32; j++) z[j] = val;
-      for (int cb = 0; cb < ncol; cb += 32) tmem_st32(ta + c0 + cb, z);
-      tmem_st_wait();
-      tc_fence_before_sync();
-    };
-
-    float dlt[3] = {0.f, 0.f, 0.f}, dlt_next[3] = {0.f, 0.f, 0.f};
-    uint32_t it = 0;
-    fetch_rows(cl);
-    publish_rows(0, dlt);
-    TE_WORKER_BARRIER();
-    if (u4 < 2) {                                   // X0, X1 clear; O2, O3 hold b2
-      fill_unit(taddr_o, 0, 128, 0u);
-      mbar_arrive(acc_init(u4));
-    } else {
-      fill_unit(taddr_o, 0, 128, __float_as_uint(bias_o));
-      mbar_arrive(out_ready);
-    }
-    if (cl + n_cl < n_items) fetch_rows(cl + n_cl);
-    for (int item = cl; item < n_items; item += n_cl, it++) {
-      const int buf = it & 1;
-      const int next = item + n_cl;
-      const bool has_next = next < n_items;
-      // the embedding rings alias the locally produced a1 stages of the previous tile, in BOTH CTAs
-      if (it > 0) mbar_wait_cluster(g2_done, (it - 1) & 1);
-      const int n = g.seg_n[item];
-      const uint32_t *t_oi = tab + buf * 256;
-      // ---- sinusoid embedding (every CTA of the pair builds all of it) ----
-      {
-        const bool valid = t_oi[r] != TE_PAD;
-#pragma unroll 1
-        for (int d = 0; d < 3; d++) {
-          float s1, c1, s48, c48, sk, ck;
-          sincospif(2.0f * dlt[d], &s1, &c1);
-          sincospif(96.0f * dlt[d], &s48, &c48);
-          sincospif((float)(32 * u4) * dlt[d], &sk, &ck);
-#pragma unroll 1
-          for (int half = 0; half < 2; half++) {
-            const int cidx = d * 2 + half;
-            const int as = u4 + 4 * (cidx & 1);
-            const uint32_t use = it * 3 + (cidx >> 1);
-            mbar_wait(a_empty(as), (use & 1) ^ 1);
-            uint8_t *slot = smem + as * TE_A_BYTES + r * 16;
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                w[e] = valid ? pack_half2(sk, ck) : 0u;
-                const float sn = fmaf(sk, c1, ck * s1);
-                const float cn = fmaf(ck, c1, -sk * s1);
-                sk = sn; ck = cn;
-              }
-              *reinterpret_cast<uint4 *>(slot + p * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            {
-              const float sn = fmaf(sk, c48, ck * s48);
-              const float cn = fmaf(ck, c48, -sk * s48);
-              sk = sn; ck = cn;
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(a_full(as));
-          }
-        }
-      }
-      TE_WORKER_BARRIER();
-      if (has_next) publish_rows(buf ^ 1, dlt_next);
-      // ---- E1: a1_v = SiLU(U + P^v_i + P^v_j) for (unit e1_m, variant e1_v), into CTA e1_v ----
-      if (tid == 0) TE_STAMP(8);
-      e1_dispatch(n, taddr_x, Pc, t_oi, t_oi + 128, a1_dst, acc1_full, it & 1);
-      if (tid == 0) TE_STAMP(9);
-      fence_proxy_async_all();                      // a1 stores (own or peer's smem) -> async proxy
-      if (e1_v == (int)rank) mbar_arrive(a1_ready); else mbar_arrive_cluster(a1_ready_dst);
-      // both variant groups have read X_{m'}: it becomes O_{m'}, pre-loaded with b2 (half the columns each)
-      tc_fence_before_sync();
-      asm volatile("bar.sync %0, 256;" ::"r"(2 + e1_m) : "memory");
-      tc_fence_after_sync();
-      fill_unit(taddr_x, e1_v * 64, 64, __float_as_uint(bias_x));
-      mbar_arrive(out_ready);
-      if (tid == 0) TE_STAMP(10);
-      TE_WORKER_BARRIER();                          // the next tile's tables are visible to everybody
-      if (has_next) prefetch_rows(buf ^ 1);
-      if (next + n_cl < n_items) fetch_rows(next + n_cl);
-      // ---- E2 (variant = rank): agg_i = mean_j SiLU(O_u); then X units are cleared, O2/O3 re-loaded with b2 ----
-      {
-        MBAR_WAIT_WORKER(acc2_full(u4), it & 1);
-        tc_fence_after_sync();
-        if (lane == 0 && q == 0) TE_STAMP(11 + 4 * u4);
-        e2_dispatch(n, taddr_o, bias_o, t_oi, out, agg_ld);
-        if (lane == 0 && q == 0) TE_STAMP(12 + 4 * u4);
-        tc_fence_before_sync();
-        if (has_next) {
-          if (u4 < 2) {
-            fill_unit(taddr_o, 0, 128, 0u);
-            mbar_arrive(acc_init(u4));
-          } else {
-            fill_unit(taddr_o, 0, 128, __float_as_uint(bias_o));
-            mbar_arrive(out_ready);
-          }
-        }
-        if (lane == 0 && q == 0) TE_STAMP(13 + 4 * u4);
-      }
-      dlt[0] = dlt_next[0]; dlt[1] = dlt_next[1]; dlt[2] = dlt_next[2];
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();               // nobody leaves while the peer may still write into this CTA
-  if (warp == 16) tmem_dealloc(tmem, 512);
-}
-
 int debug_edge_timeline(long long *out96) {
   CB2_CUDA_OK(cudaMemcpyFromSymbol(out96, g_edge_dbg, sizeof(long long) * 3 * 96));
   return CB2_OK;
@@ -949,28 +611,8 @@ int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {
   if (n_items == 0) return CB2_OK;
   if ((uint64_t)a.V * (uint64_t)a.N * (uint64_t)H2 >= (1ull << 32))
     return fail(CB2_ERR_UNSUPPORTED, "tensor-core edge kernel: V*N*1024 must fit 32 bits (shard the batch)");
-  static bool attr_set = false;
-  static int pair_mode = -1;        // CB2_EDGE_PAIR=1 selects the CTA-pair kernel (see below); default off
-  if (!attr_set) {
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
-    const char *e = getenv("CB2_EDGE_PAIR");
-    pair_mode = (e && atoi(e) == 1) ? 1 : 0;
-    attr_set = true;
-  }
-  if (a.V == 2 && pair_mode == 1) {
-    // Both CFG variants on CTA pairs, GEMM1 shared between them.  Correct (same results as
-    // k_tc_edge) but NOT the default: measured 4.16-4.43 ms against 4.2-4.3 ms at C3.  Per tile
-    // and CTA the MMA work drops from 20.5 k to 14.3 k cycles, but the embedding producers
-    // (10.7 k cycles for 24 chunks) now bound the GEMM1 phase and the a1 exchange through
-    // distributed shared memory lengthens E1 by ~3 k cycles; sharing the embedding between the
-    // CTAs as well (remote stores + cross-CTA slot hand-shake) made it 15 % slower still.
-    int n_cl = n_sm / 2;
-    if (a.n_tiles < n_cl) n_cl = a.n_tiles;
-    k_tc_edge_pair<<<2 * n_cl, TE_THREADS, TE_SMEM, st>>>(a);
-    CB2_LAUNCH_OK("k_tc_edge_pair");
-    return CB2_OK;
-  }
+  // per-device function attribute: set on every launch (cheap, legal during stream capture)
+  CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
   const int grid = n_items < n_sm ? n_items : n_sm;
   k_tc_edge<<<grid, TE_THREADS, TE_SMEM, st>>>(a);
   CB2_LAUNCH_OK("k_tc_edge");

@@ -344,11 +344,7 @@ int launch_tc_film(const cb2_model *m, const cb2_layer_weights &L, const cb2_bat
                    const __half *h16, float *h, __half *cat16, int n_sm, cudaStream_t st) {
   const int64_t VN = (int64_t)b->n_variants * b->n_nodes;
   if (VN == 0) return CB2_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_film, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
-    attr_set = true;
-  }
+  CB2_CUDA_OK(cudaFuncSetAttribute(k_tc_film, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));   // per device
   TcFilmArgs a{};
   a.A = h16; a.M = VN; a.Wt = (const __half *)m->film_wp_t; a.bias = m->film_bp;
   a.g1 = m->film_g; a.b1 = m->film_b; a.g2 = L.ln_g; a.b2 = L.ln_b;

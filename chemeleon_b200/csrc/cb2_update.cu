@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_update_predictor(UpdateParams p) {
       float xo = p.x[(int64_t)n * 3 + lane];
       float xn = __fadd_rn(__fsub_rn(xo, __fmul_rn(cf[3], pxs)), __fmul_rn(cf[4], z));
       p.x[(int64_t)n * 3 + lane] = xn;
-      if (!isfinite(xn)) p.flags[g] = 1;
+      if (!isfinite(xn)) atomicOr(p.flags + g, CB2_FLAG_NONFINITE);
     }
   } else if (w < (int64_t)p.N + p.B) {
     // ---- lattice ancestral step: lanes 0..8 ----
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_update_predictor(UpdateParams p) {
       ln = mask ? ln : 0.f;
       if (t == p.T) ln = fminf(fmaxf(ln, -6.0f), 6.0f);
       p.l[(int64_t)g * 9 + lane] = ln;
-      if (!isfinite(ln)) p.flags[g] = 1;
+      if (!isfinite(ln)) atomicOr(p.flags + g, CB2_FLAG_NONFINITE);
     }
   }
 }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) k_update_corrector(UpdateParams p) {
   float xn = __fadd_rn(__fsub_rn(xh, __fmul_rn(cf[6], pxs)), __fmul_rn(cf[7], z));
   xn = wrap01(xn);
   p.x[idx] = xn;
-  if (!isfinite(xn)) p.flags[p.node2graph[n]] = 1;
+  if (!isfinite(xn)) atomicOr(p.flags + p.node2graph[n], CB2_FLAG_NONFINITE);
 }
 
 __global__ void k_advance_t(int32_t *t_dev) { *t_dev = *t_dev - 1; }

@@ -79,6 +79,40 @@ def gather_structures(a: torch.Tensor, x: torch.Tensor, l: torch.Tensor, natoms:
     return A, X, L
 
 
+class ShardPlan:
+    """Which samples (and nodes) of a global ragged batch this rank owns."""
+
+    def __init__(self, natoms: Sequence[int], world: int, rank: int):
+        self.natoms = [int(n) for n in natoms]
+        self.world, self.rank = int(world), int(rank)
+        self.parts = partition_samples(self.natoms, self.world)
+        self.mine = self.parts[self.rank]
+        self.my_natoms = [self.natoms[i] for i in self.mine]
+        self.my_nodes = node_slices(self.natoms, self.mine)
+        self.B, self.N = len(self.natoms), sum(self.natoms)
+
+    def cost(self, r: Optional[int] = None) -> float:
+        return sum(sample_cost(self.natoms[i]) for i in self.parts[self.rank if r is None else r])
+
+
+def prepare_sharded_run(model, plan: ShardPlan, text_embeds: Optional[torch.Tensor],
+                        null_text_embeds: Optional[torch.Tensor], cond_scale: float = 2.0, step_lr: float = 1e-5,
+                        seed: int = 0, t_start: Optional[int] = None):
+    """This rank's `SamplerRun` (captured CUDA graph, conditioning, Philox keys = GLOBAL sample ids)
+    with its initial state set from the global-order initial noise (sharding invariant)."""
+    with torch.cuda.device(model.device):
+        l_T, x_T = model.initial_noise(plan.B, plan.N, seed)   # global order on every rank
+        nodes = torch.from_numpy(plan.my_nodes).to(x_T.device)
+        gi = torch.tensor(plan.mine, dtype=torch.int64, device=x_T.device)
+        te = text_embeds[gi.to(text_embeds.device)] if text_embeds is not None else None
+        ne = null_text_embeds
+        if ne is not None and ne.shape[0] == plan.B and plan.B != 1:
+            ne = ne[gi.to(ne.device)]
+        run = model.make_run(plan.my_natoms, te, ne, cond_scale, step_lr, None, seed, plan.mine)
+        run.init_state(l_T[gi], x_T[nodes], t_start)
+    return run
+
+
 def sample_sharded(model, natoms: Sequence[int], text_embeds: Optional[torch.Tensor],
                    null_text_embeds: Optional[torch.Tensor], cond_scale: float = 2.0, step_lr: float = 1e-5,
                    seed: int = 0, t_stop: int = 0, group=None, gather: bool = True):
@@ -86,24 +120,18 @@ def sample_sharded(model, natoms: Sequence[int], text_embeds: Optional[torch.Ten
     if `gather`, all ranks return the full (a, x, l) in the caller's sample order."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    natoms = [int(n) for n in natoms]
-    parts = partition_samples(natoms, world)
-    mine = parts[rank]
-    B, N = len(natoms), sum(natoms)
-    l_T, x_T = model.initial_noise(B, N, seed)   # global order on every rank => sharding invariant
-    nodes = torch.from_numpy(node_slices(natoms, mine)).to(x_T.device)
-    gi = torch.tensor(mine, dtype=torch.int64, device=x_T.device)
-    te = text_embeds[gi.to(text_embeds.device)] if text_embeds is not None else None
-    ne = null_text_embeds
-    if ne is not None and ne.shape[0] == B:
-        ne = ne[gi.to(ne.device)]
-    a, x, l = model.sample_states([natoms[i] for i in mine], te, ne, cond_scale, step_lr, seed=seed,
-                                  t_stop=t_stop, graph_gid=mine, init_noise=(l_T[gi], x_T[nodes]))
-    if not gather or world == 1:
-        if world == 1:
-            return gather_local(a, x, l, natoms, parts)
-        return a, x, l
-    return gather_structures(a, x, l, natoms, parts, group)
+    plan = ShardPlan(natoms, world, rank)
+    with torch.cuda.device(model.device):
+        run = prepare_sharded_run(model, plan, text_embeds, null_text_embeds, cond_scale, step_lr, seed)
+        for _ in range(model.cfg.timesteps, t_stop, -1):
+            run.step()
+        a, x, l = run.get_state()
+        model.last_flags = run.flags.clone()
+        if not gather or world == 1:
+            if world == 1:
+                return gather_local(a, x, l, plan.natoms, plan.parts)
+            return a, x, l
+        return gather_structures(a, x, l, plan.natoms, plan.parts, group)
 
 
 def gather_local(a, x, l, natoms, parts):

@@ -77,7 +77,7 @@ class DecoderEngine:
         return t
 
     def workspace(self, topo: BatchTopology) -> torch.Tensor:
-        need = int(self.lib.cb2_workspace_bytes(topo.byref(), self.precision))
+        need = int(self.lib.cb2_workspace_bytes(C.byref(self.model), topo.byref(), self.precision))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -127,6 +127,9 @@ class DecoderEngine:
         io.head_out, io.lattice_out, io.node_features = head.data_ptr(), lat.data_ptr(), _lib.ptr(feat)
         io.coords_only = int(coords_only)
         io.precision = self.precision
+        # guard bits per crystal (CB2_FLAG_TC_RANGE: cell outside the fp16 range of the tensor-core path)
+        self.last_flags = torch.zeros(max(B, 1), device=dev, dtype=torch.int32)
+        io.flags = self.last_flags.data_ptr()
         _lib.check(self.lib.cb2_decoder_forward(C.byref(self.model), topo.byref(), C.byref(io), ws.data_ptr(),
                                                 ws.numel(), _stream_ptr()), "cb2_decoder_forward")
         return head, lat, feat

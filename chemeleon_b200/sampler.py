@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from typing import Callable, Iterator, List, Optional, Sequence, Union
 
 import numpy as np
@@ -104,6 +105,8 @@ class SamplerRun:
         self.args = args
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
+        self.t_host = 0          # host mirror of the device timestep counter (guards against stepping past t = 1)
+        self.busy = False        # owned by a live generator: must not be handed out again from the run cache
 
     # -- re-use of a captured run with new conditioning (pointers stay valid) -------
     def reconfigure(self, text: Optional[torch.Tensor], null_text: Optional[torch.Tensor], seed: int,
@@ -126,6 +129,7 @@ class SamplerRun:
         self.x.copy_(x.to(dev, torch.float32))
         self.l.copy_(l.to(dev, torch.float32).reshape(-1, 9))
         self.t_dev.fill_(int(t))
+        self.t_host = int(t)
         self.flags.zero_()
 
     def init_state(self, l_T: torch.Tensor, x_T: torch.Tensor, t_start: Optional[int] = None) -> None:
@@ -153,6 +157,8 @@ class SamplerRun:
         saved = (self.a.clone(), self.x.clone(), self.l.clone(), self.t_dev.clone(), self.flags.clone())
         if int(saved[3].item()) < 1:
             self.t_dev.fill_(1)
+        if self.noise is not None:   # keep the warm-up / capture steps inside the injected tensors
+            self.t_dev.fill_(self.noise.t_start)
         s = torch.cuda.Stream(device=self.eng.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -169,6 +175,13 @@ class SamplerRun:
         self._graph = g
 
     def step(self) -> None:
+        if self.t_host < 1:
+            raise RuntimeError("SamplerRun.step(): the run is finished (t < 1); call set_state/init_state first")
+        if self.noise is not None and self.t_host > self.noise.t_start:
+            raise RuntimeError("SamplerRun.step(): timestep above the first slice of the injected noise")
+        if self.noise is not None and self.noise.t_start - self.t_host >= self._noise_dev[0].shape[0]:
+            raise RuntimeError("SamplerRun.step(): injected noise tensors are exhausted")
+        self.t_host -= 1
         if self.use_cuda_graph:
             if self._graph is None:
                 self.capture()
@@ -247,9 +260,13 @@ class ChemeleonB200:
         # shape (e.g. composition sweeps); only the conditioning, seed and sample ids change.
         key = (tuple(int(n) for n in natoms), float(cond_scale), float(step_lr))
         run = self._run_cache.get(key)
+        if run is not None and run.busy:
+            # a live generator (stream=True) owns the cached run: its state must not be shared
+            return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, None, seed,
+                              graph_gid, self.use_cuda_graph)
         if run is None:
             if len(self._run_cache) >= 4:
-                self._run_cache.clear()
+                self._run_cache = {k: r for k, r in self._run_cache.items() if r.busy}
             run = SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, None, seed,
                              graph_gid, self.use_cuda_graph)
             self._run_cache[key] = run
@@ -293,6 +310,20 @@ class ChemeleonB200:
             self.last_flags = run.flags.clone()
         return a, x, l
 
+    def check_flags(self, flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Guard bits of the last run (host int32 [B]); warns when any crystal is flagged.
+        Bit 1 (`_lib.FLAG_NONFINITE`): the update produced NaN/Inf; bit 2 (`_lib.FLAG_TC_RANGE`):
+        tensor-core mode met a cell outside its fp16 range -- re-run those samples with precision="fp32"."""
+        f = (self.last_flags if flags is None else flags).cpu()
+        bad = int((f != 0).sum())
+        if bad:
+            nf = int(((f & _lib.FLAG_NONFINITE) != 0).sum())
+            rg = int(((f & _lib.FLAG_TC_RANGE) != 0).sum())
+            warnings.warn(f"chemeleon_b200: {bad} of {f.numel()} structures are flagged "
+                          f"({nf} non-finite, {rg} outside the tensor-core range); see ChemeleonB200.last_flags",
+                          RuntimeWarning, stacklevel=2)
+        return f
+
     def _to_atoms(self, a, x, l, natoms):
         return state_to_atoms(a.cpu().numpy(), x.cpu().numpy(), l.reshape(-1, 9).cpu().numpy(), natoms)
 
@@ -312,13 +343,18 @@ class ChemeleonB200:
         natoms = [int(n) for n in natoms]
         with torch.cuda.device(self.device):
             run = self.make_run(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed)
-            if noise is not None:
-                run.init_state(noise.l_T, noise.x_T)
-            else:
-                run.init_state(*self.initial_noise(run.B, run.N, seed))
-            for _t in range(self.cfg.timesteps, 0, -1):
-                run.step()
-                yield self._to_atoms(run.a, run.x, run.l, natoms)
+            run.busy = True
+            try:
+                if noise is not None:
+                    run.init_state(noise.l_T, noise.x_T)
+                else:
+                    run.init_state(*self.initial_noise(run.B, run.N, seed))
+                for _t in range(self.cfg.timesteps, 0, -1):
+                    run.step()
+                    yield self._to_atoms(run.a, run.x, run.l, natoms)
+                self.last_flags = run.flags.clone()
+            finally:
+                run.busy = False
 
     def sample(self, text_input: str, n_atoms: int, n_samples: int, cond_scale: float = 2.0,
                step_lr: float = 1e-5, return_trajectory: bool = False, stream: bool = False, **kw):
@@ -332,13 +368,17 @@ class ChemeleonB200:
 
     def sample_batch(self, natoms: Sequence[int], texts: Optional[Sequence[str]] = None, *, text_embeds=None,
                      null_text_embeds=None, cond_scale: float = 2.0, step_lr: float = 1e-5, noise=None,
-                     seed: int = 0):
+                     seed: int = 0, t_stop: int = 0, return_flags: bool = False):
         """Ragged entry point (the use-case of the reference's stale list-based callers,
-        scripts/evaluate.py:97-99): final structures only, one D2H at the end."""
+        scripts/evaluate.py:97-99): final structures only, one D2H at the end.  The per-crystal guard
+        bits are checked (RuntimeWarning) and returned with `return_flags=True`."""
         if self.text_guide and text_embeds is None:
             text_embeds, null_text_embeds = self._embed_texts(texts)
-        a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed)
-        return self._to_atoms(a, x, l, [int(n) for n in natoms])
+        a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed,
+                                     t_stop=t_stop)
+        flags = self.check_flags()
+        atoms = self._to_atoms(a, x, l, [int(n) for n in natoms])
+        return (atoms, flags) if return_flags else atoms
 
     def sample_batch_valid(self, natoms: Sequence[int], texts: Optional[Sequence[str]] = None, *,
                            target_composition: Optional[str] = None, max_length: float = 60.0,
@@ -353,7 +393,9 @@ class ChemeleonB200:
         if self.text_guide and text_embeds is None:
             text_embeds, null_text_embeds = self._embed_texts(texts)
         a, x, l = self.sample_states(natoms, text_embeds, null_text_embeds, **kw)
-        flags, _, _ = validity_flags(a, x, l, natoms, target_composition, max_length, min_distance)
+        self.check_flags()
+        with torch.cuda.device(self.device):
+            flags, _, _ = validity_flags(a, x, l, natoms, target_composition, max_length, min_distance)
         flags = flags.cpu()
         atoms = self._to_atoms(a, x, l, natoms)
         return [at for at, f in zip(atoms, flags.tolist()) if f == 0], flags

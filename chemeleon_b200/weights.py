@@ -31,7 +31,8 @@ Tensor = torch.Tensor
 
 
 def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, head_scale: float = 1.0,
-                           perturb_ln: bool = True, lattice_identity: bool = False) -> Dict[str, Tensor]:
+                           perturb_ln: bool = True, lattice_identity: bool = False,
+                           lattice_gamma: float = 1.0) -> Dict[str, Tensor]:
     """Random weights of the reference architecture, keyed like its checkpoint.
 
     Checkpoints are not available offline, so benchmarks and parity tests use
@@ -80,9 +81,12 @@ def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, 
         # run.  Make the head behave like a trained denoiser for data at the origin:
         # feature 0 of the final LayerNorm is the constant 4 and lattice_out maps it to
         # vec(I)/4, so lattice_out ~= I @ L and the step is a contraction (|l| stays O(1)).
+        # `lattice_gamma` < 1 weakens the contraction (lattice_out ~= gamma L): with 0.5 the cosine
+        # schedule holds the lattice entries at 5..20 for the WHOLE run, i.e. cells of 8..25 A with
+        # shear -- the regime a trained model's raw-Angstrom lattices live in (dataset_utils.py:25).
         sd["decoder.final_layer_norm.weight"][0] = 0.0
         sd["decoder.final_layer_norm.bias"][0] = 4.0
-        sd["decoder.lattice_out.weight"][:, 0] = torch.eye(3).reshape(9) / 4.0
+        sd["decoder.lattice_out.weight"][:, 0] = lattice_gamma * torch.eye(3).reshape(9) / 4.0
     sx = schedules.sigma_buffer(cfg.timesteps, cfg.sigma_begin, cfg.sigma_end)
     sd["sigma_scheduler.sigmas"] = sx
     sd["sigma_scheduler.sigmas_norm"] = schedules.sigma_norm_monte_carlo(sx[1:], seed=seed)

@@ -10,7 +10,9 @@
  * Conventions
  *  - plain C: POD structs of raw pointers + sizes, no torch / C++ types;
  *  - every buffer (weights, state, outputs, workspace) is CALLER-OWNED; the
- *    library never allocates or frees device memory;
+ *    library never allocates or frees device memory and keeps no per-process
+ *    configuration (no environment switches; the only process-wide state is the
+ *    thread-local error string and the launch counter);
  *  - pointers are DEVICE pointers unless the field name starts with `host_`;
  *  - kernels are enqueued on the given stream (a cudaStream_t passed as void*)
  *    and never synchronise, so every call is CUDA-graph capturable;
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CB2_ABI_VERSION 1
+#define CB2_ABI_VERSION 2
 #define CB2_HIDDEN 512
 #define CB2_MAX_LAYERS 16
 #define CB2_MAX_ATOM_TYPES 104
@@ -94,7 +96,12 @@ typedef struct {
   const void *w_head_t;         /* tensor-core heads (may be NULL: fp32 SIMT heads): 16-byte header {float 1/s}, then the
                                  * fp16 K-major image [192][256][8] of s*[w_hi | w_hi | w_lo] (split precision, rows >= 128 zero) */
   const float *w_lat;           /* [9,512] lattice_out.weight */
+  int32_t flags;                /* CB2_MODEL_* bits, 0 = defaults */
 } cb2_model;
+
+/* cb2_model.flags */
+#define CB2_MODEL_EDGE_SINGLE_CTA 1  /* V == 2: run the one-CTA edge kernel per variant instead of the CTA-pair
+                                      * kernel that shares the sinusoid GEMM between the variants (A/B testing) */
 
 /* ---- topology of one ragged batch; fixed for a whole sampling run ----
  * Replaces CSPNet.gen_edges (cspnet.py:319-324): edges are implied by the
@@ -135,7 +142,16 @@ typedef struct {
   float *node_features;        /* [V*N,512] after final LN (may be NULL) */
   int32_t coords_only;         /* corrector call: lattice head skipped */
   int32_t precision;           /* cb2_precision */
+  int32_t *flags;              /* [B] optional: CB2_FLAG_TC_RANGE is OR-ed in for crystals outside the fp16 range */
 } cb2_forward_io;
+
+/* per-crystal guard flags (cb2_state.flags, cb2_forward_io.flags) */
+#define CB2_FLAG_NONFINITE 1   /* the update produced NaN/Inf for this crystal */
+#define CB2_FLAG_TC_RANGE 2    /* tensor-core mode only: |W_ip vec(L L^T) + b1| > CB2_TC_RANGE_LIMIT, i.e. the edge
+                                * pre-activations leave the range of the fp16 GEMM2 operand (cells of several
+                                * hundred Angstrom; the reference itself discards cells > 60 A, evaluate.py:180).
+                                * Results for such a crystal are not covered by the 1e-3 tolerance: use exact mode. */
+#define CB2_TC_RANGE_LIMIT 16384.0f
 
 /* ---- sampler state + one reverse-diffusion timestep (chemeleon.py:379-467) ---- */
 typedef struct {
@@ -143,7 +159,7 @@ typedef struct {
   float *frac_coords;          /* [N,3] x_t -> x_{t-1} (wrapped) */
   float *lattices;             /* [B,9] l_t -> l_{t-1} */
   int32_t *t_dev;              /* device scalar: current timestep; decremented by the step */
-  int32_t *flags;              /* [B] non-finite guard, 1 = crystal produced NaN/Inf */
+  int32_t *flags;              /* [B] guard bits CB2_FLAG_* (OR-ed in, never cleared by the library) */
 } cb2_state;
 
 typedef struct {
@@ -170,8 +186,8 @@ int cb2_abi_version(void);
 const char *cb2_last_error(void);
 int cb2_check_device(int device);            /* CB2_OK iff compute capability 10.x */
 
-/* Workspace one forward / step needs for this batch (bytes). */
-size_t cb2_workspace_bytes(const cb2_batch *batch, int precision);
+/* Workspace one forward / step of model `m` needs for this batch (bytes). */
+size_t cb2_workspace_bytes(const cb2_model *m, const cb2_batch *batch, int precision);
 
 /* h = node_embedding(atom_types); replaces cspnet.py:357 (also used by tests). */
 int cb2_embed_nodes(const cb2_model *m, const cb2_batch *b, const int64_t *atom_types,
@@ -188,18 +204,22 @@ int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bia
 
 /* C = act(A16 W16^T + bias) on the tensor cores (tcgen05, fp32 accumulate).  A16: fp16
  * row-major [M,lda]; Wt: fp16 operand image [K/8][Nw][8] of a torch Linear weight [Nw,K]
- * (weights.tile_k_major); K % 64 == 0, Nw % 256 == 0, lda % 8 == 0 (A is re-tiled into the row-panel layout of the pipeline first).  The building block of the
+ * (weights.tile_k_major); K % 64 == 0, Nw % 256 == 0, lda % 8 == 0 (A is re-tiled into the row-panel layout of the pipeline first, into the caller's workspace).  The building block of the
  * node-level GEMMs (FilmLayer.proj, hoisted W1 blocks, node_mlp; cspnet.py:86,113,120). */
 int cb2_linear_tc(const void *A16, int64_t lda, const void *Wt, int32_t Nw, const float *bias, float *C,
-                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *stream);
+                  int64_t ldc, int64_t M, int32_t K, int32_t silu, void *workspace, size_t workspace_bytes,
+                  void *stream);
+/* ... its workspace (the row-panel copy of A): bytes for an [M,K] operand. */
+size_t cb2_linear_tc_workspace_bytes(int64_t M, int32_t K);
 
 /* Edge model + scatter_mean of ONE CSPLayer (CSPLayer.edge_model + the aggregation in
- * node_model, cspnet.py:129-160) from the hoisted node terms P [V*N,1024] = (P_i | P_j):
- *   agg_i = mean_j SiLU(W2 SiLU(P_i[i] + P_j[j] + W_fd emb(x_j - x_i)) + b2).
+ * node_model, cspnet.py:129-160) from the hoisted node terms P [V*N,1024] = (P_i | P_j) = hn [W_hi;W_hj]^T
+ * and the per-crystal lattice term cg [B,512] = W_ip vec(L L^T) + b1 (fp32 in both modes; NULL = 0):
+ *   agg_i = mean_j SiLU(W2 SiLU(P_i[i] + cg[graph(i)] + P_j[j] + W_fd emb(x_j - x_i)) + b2).
  * precision FP32: P and agg are float; TC_F16: P and agg are fp16 (row-major, leading dimensions
  * 1024 and ld_agg). */
 int cb2_edge_layer(const cb2_model *m, int32_t layer, const cb2_batch *b, const float *frac_coords,
-                   const void *P, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
+                   const void *P, const float *cg, void *agg, int64_t ld_agg, int32_t precision, void *workspace,
                    size_t workspace_bytes, void *stream);
 
 /* One CSPNet.forward (cspnet.py:345-405) for all V variants of the batch. */

@@ -18,9 +18,12 @@ N = topo.N
 x = torch.rand(N, 3, device="cuda")
 P = torch.randn(2 * N, 1024, device="cuda").half()
 agg = torch.empty(2 * N, 512, device="cuda", dtype=torch.float16)
+cg = torch.randn(topo.B, 512, device="cuda")
+if os.environ.get("CB2_SINGLE_CTA"):
+    eng.model.flags |= _lib.MODEL_EDGE_SINGLE_CTA
 def once():
-    _lib.check(eng.lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), agg.data_ptr(),
-                                      512, 1, None, 0, torch.cuda.current_stream().cuda_stream), "edge")
+    _lib.check(eng.lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(), cg.data_ptr(),
+                                      agg.data_ptr(), 512, 1, None, 0, torch.cuda.current_stream().cuda_stream), "edge")
 once(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -40,11 +40,12 @@ def weight_checksum(sd):
 
 
 def run_case(name, natoms, weight_seed, head_scale, noise_seed, text_seed, n_steps, record_ts, state_ts,
-             cond_scale=2.0, step_lr=1e-5, lattice_identity=False):
+             cond_scale=2.0, step_lr=1e-5, lattice_identity=False, lattice_gamma=1.0):
     ref = ref_shim.load_reference()
     model = ref_shim.build_reference_model(0)
     cfg = SamplerConfig()
-    sd = random_init_state_dict(cfg, seed=weight_seed, head_scale=head_scale, lattice_identity=lattice_identity)
+    sd = random_init_state_dict(cfg, seed=weight_seed, head_scale=head_scale, lattice_identity=lattice_identity,
+                                lattice_gamma=lattice_gamma)
     res = model.load_state_dict(sd, strict=False)
     assert not [k for k in res.missing_keys if k.startswith(("decoder.", "sigma_scheduler."))], res
     B, N = len(natoms), sum(natoms)
@@ -83,7 +84,7 @@ def run_case(name, natoms, weight_seed, head_scale, noise_seed, text_seed, n_ste
     out = dict(
         natoms=np.array(natoms, dtype=np.int64), weight_seed=np.int64(weight_seed),
         head_scale=np.float64(head_scale), noise_seed=np.int64(noise_seed),
-        lattice_identity=np.int64(int(lattice_identity)),
+        lattice_identity=np.int64(int(lattice_identity)), lattice_gamma=np.float64(lattice_gamma),
         cond_scale=np.float64(cond_scale), step_lr=np.float64(step_lr), n_steps=np.int64(n_steps),
         text=text.numpy(), null_text=null.numpy(), weight_checksum=weight_checksum(sd),
         sigmas_norm=sd["sigma_scheduler.sigmas_norm"].numpy(),
@@ -101,6 +102,44 @@ def run_case(name, natoms, weight_seed, head_scale, noise_seed, text_seed, n_ste
         out[f"rec{t}_pred_a"], out[f"rec{t}_pred_l"], out[f"rec{t}_pred_x"] = pa.numpy(), pl.numpy(), px.numpy()
         out[f"rec{t}_pred_x2"] = px2.numpy()
         out[f"rec{t}_a_next"], out[f"rec{t}_x_next"], out[f"rec{t}_l_next"] = an.numpy(), xn.numpy(), ln.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def run_forward_cases(name="ang_forward"):
+    """`CSPNet.forward` of the unmodified reference on hand-built states with PHYSICAL cells:
+    lengths 3..25 A plus shear (the raw-Angstrom lattices the reference feeds its decoder,
+    datasets/dataset_utils.py:25), n in {6, 20, 40} and a ragged mix."""
+    ref_shim.load_reference()
+    model = ref_shim.build_reference_model(0)
+    cfg = SamplerConfig()
+    out = {}
+    cases = [("n6", [6, 6, 6]), ("n20", [20, 20]), ("n40", [40, 40]), ("ragged", [40, 33, 4, 1, 20])]
+    for ci, (tag, natoms) in enumerate(cases):
+        sd = random_init_state_dict(cfg, seed=20 + ci)
+        res = model.load_state_dict(sd, strict=False)
+        assert not [k for k in res.missing_keys if k.startswith("decoder.")], res
+        B, N = len(natoms), sum(natoms)
+        g = torch.Generator().manual_seed(100 + ci)
+        abc = 3.0 + 22.0 * torch.rand(B, 3, generator=g)                      # 3..25 A
+        l = torch.diag_embed(abc)
+        shear = (torch.rand(B, 3, 3, generator=g) - 0.5) * 0.6 * abc[:, :, None]   # up to +-30 % of the length
+        l = l + shear * (1 - torch.eye(3))
+        a = torch.randint(0, 104, (N,), generator=g)
+        x = torch.rand(N, 3, generator=g)
+        t = torch.randint(1, 1001, (B,), generator=g)
+        text = torch.randn(B, cfg.text_dim, generator=g)
+        nat = torch.tensor(natoms)
+        bi = torch.arange(B).repeat_interleave(nat)
+        with torch.no_grad():
+            temb = model.time_embed(t)
+            o = model.decoder(a, x, l, nat, bi, t=temb, text_embeds=text)
+        for k, v in dict(natoms=nat, a=a, x=x, l=l, t=t, text=text, types=o.atom_types_out, lattice=o.lattice_out,
+                         coords=o.coords_out, weight_seed=torch.tensor(20 + ci),
+                         weight_checksum=torch.from_numpy(weight_checksum(sd))).items():
+            out[f"{tag}_{k}"] = v.numpy()
+    out["cases"] = np.array([c[0] for c in cases])
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
@@ -126,6 +165,20 @@ if __name__ == "__main__":
     # free-running trajectory stays bounded and the final structure is meaningful.
     run_case("c1_tamed_1000", [6, 6, 6], weight_seed=0, head_scale=0.01, noise_seed=7, text_seed=1,
              n_steps=1000, record_ts=[1000, 999, 500, 2, 1], state_ts=[1000, 999, 998, 970, 500, 30, 2, 1, 0])
+    # Angstrom regime: lattice_gamma = 0.5 keeps the lattice entries at 5..20 (cells of 8..25 A with
+    # shear, |L L^T| ~ 1e2..1e3) for all 1000 steps -- the tensor-core path's per-crystal lattice term
+    # W_ip vec(L L^T) is O(10..100) here.  Config 1 for the full run, n = 20 / n = 40 for the first steps.
+    run_case("ang_c1_1000", [6, 6, 6], weight_seed=0, head_scale=0.01, noise_seed=7, text_seed=1,
+             n_steps=1000, record_ts=[1000, 999, 700, 400, 100, 2, 1], state_ts=[1000, 999, 700, 400, 100, 2, 1, 0],
+             lattice_identity=True, lattice_gamma=0.5)
+    run_case("ang_n20_6", [20, 20, 20], weight_seed=5, head_scale=0.01, noise_seed=17, text_seed=2,
+             n_steps=6, record_ts=[1000, 999, 996], state_ts=[1000, 999, 998, 996, 995, 994],
+             lattice_identity=True, lattice_gamma=0.5)
+    run_case("ang_n40_4", [40, 33, 6], weight_seed=6, head_scale=0.01, noise_seed=19, text_seed=3,
+             n_steps=4, record_ts=[1000, 999, 997], state_ts=[1000, 999, 998, 997, 996],
+             lattice_identity=True, lattice_gamma=0.5)
+    if not only or "ang_forward" in only:
+        run_forward_cases()
     # full-scale heads, first steps only (the dynamics blow up later with random weights)
     run_case("c1_full_6", [6, 6, 6], weight_seed=0, head_scale=1.0, noise_seed=7, text_seed=1,
              n_steps=6, record_ts=[1000, 999, 995], state_ts=[1000, 999, 998, 995, 994])

@@ -45,8 +45,8 @@ def test_struct_layouts_match_header():
 int main(void){
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(cb2_layer_weights), sizeof(cb2_model), sizeof(cb2_batch),
          sizeof(cb2_forward_io), sizeof(cb2_state), sizeof(cb2_step_args), offsetof(cb2_model, final_g));
-  printf("%zu %zu %zu %zu\n", offsetof(cb2_batch, host_chunk_node_lo), offsetof(cb2_batch, tile_row_i),
-         offsetof(cb2_step_args, rand_a), offsetof(cb2_step_args, graph_gid));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(cb2_batch, host_chunk_node_lo), offsetof(cb2_batch, tile_row_i),
+         offsetof(cb2_step_args, rand_a), offsetof(cb2_step_args, graph_gid), offsetof(cb2_model, flags));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -59,7 +59,7 @@ int main(void){
     want = [C.sizeof(_lib.LayerWeights), C.sizeof(_lib.Model), C.sizeof(_lib.Batch), C.sizeof(_lib.ForwardIO),
             C.sizeof(_lib.State), C.sizeof(_lib.StepArgs), _lib.Model.final_g.offset,
             _lib.Batch.host_chunk_node_lo.offset, _lib.Batch.tile_row_i.offset, _lib.StepArgs.rand_a.offset,
-            _lib.StepArgs.graph_gid.offset]
+            _lib.StepArgs.graph_gid.offset, _lib.Model.flags.offset]
     assert got == want
 
 
@@ -71,9 +71,9 @@ def test_bad_arguments_fail_loudly(lib):
     io = _lib.ForwardIO()
     assert lib.cb2_decoder_forward(C.byref(m), C.byref(b), C.byref(io), None, 0, None) != 0
     assert b"abi_version" in lib.cb2_last_error()
-    m.abi_version, m.hidden, m.n_atom_types, m.n_freqs, m.n_layers = 1, 256, 104, 128, 6
+    m.abi_version, m.hidden, m.n_atom_types, m.n_freqs, m.n_layers = _lib.ABI_VERSION, 256, 104, 128, 6
     assert lib.cb2_decoder_forward(C.byref(m), C.byref(b), C.byref(io), None, 0, None) == -2  # unsupported shape
-    assert lib.cb2_workspace_bytes(None, 0) == 0
+    assert lib.cb2_workspace_bytes(None, None, 0) == 0
 
 
 def test_no_gpu_means_no_fallback():

@@ -1,9 +1,14 @@
 """GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle
 and the committed golden fixtures of the unmodified reference.
 
-Tolerances (relative = max|a-b| / max|b|):
+Tolerances (relative = max|a-b| / max|b| over the whole tensor, helpers.rel_err):
   * fp32 exact mode: 1e-4 on decoder outputs (observed ~1e-6), types bit-exact on fixtures
-  * tensor-core mode (fp16 operands, fp32 accumulate): 1e-3, the north-star tolerance
+  * tensor-core mode (fp16 operands, fp32 accumulate): 1e-3, the north-star tolerance;
+    sampled types >= 0.99 match (observed 1.0)
+Fixtures cover the O(1) lattices of the first timesteps AND the Angstrom regime (cells of
+8..25 A with shear, ang_*).  States whose lattice term exceeds the tensor-core range
+(CB2_TC_RANGE_LIMIT; only reachable with untrained weights: c1_tamed_1000 at t <= 500 has
+cells of thousands of Angstrom) must raise CB2_FLAG_TC_RANGE instead of being trusted.
 """
 import ctypes as C
 
@@ -11,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, golden_weights, load_golden, rel_err
+from helpers import GOLDEN_CASES, forward_golden_cases, golden_weights, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -203,11 +208,23 @@ def test_update_kernels_vs_oracle(O, t):
     assert int(keep[1].item()) == t - 1  # device-side timestep counter advanced
 
 
-def _out_of_fp16_range(g, t):
-    """The tensor-core path keeps activations in fp16 (max 65504).  With untrained weights the
-    lattice of the 'tamed' fixtures grows to ~1e3 (L L^T ~ 1e7), far outside any trained
-    regime; those states are checked in exact mode only (precision)."""
-    return float(np.abs(g[f"rec{t}_l_t"]).max()) > 50.0
+def _lattice_term_max(sd, l):
+    """max over layers / crystals / channels of |W_ip vec(L L^T) + b1| (what cb2 compares with
+    CB2_TC_RANGE_LIMIT), per crystal."""
+    l = torch.as_tensor(l, dtype=torch.float64).reshape(-1, 3, 3)
+    ip = (l @ l.transpose(1, 2)).reshape(-1, 9)
+    worst = torch.zeros(l.shape[0], dtype=torch.float64)
+    for i in range(6):
+        w1 = sd[f"decoder.csp_layer_{i}.edge_mlp.0.weight"].double()
+        cg = ip @ w1[:, 1024:1033].t() + sd[f"decoder.csp_layer_{i}.edge_mlp.0.bias"].double()
+        worst = torch.maximum(worst, cg.abs().max(dim=1).values)
+    return worst
+
+
+def _tc_out_of_range(sd, l):
+    from chemeleon_b200 import _lib
+
+    return _lattice_term_max(sd, l) > _lib.TC_RANGE_LIMIT
 
 
 def _golden_noise(O, g, t_hi, t_lo):
@@ -232,27 +249,56 @@ def test_golden_teacher_forced_steps(O, precision, case):
     natoms = g["natoms"].tolist()
     text, null = torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"])
     tol = TOL[precision]
+    from chemeleon_b200 import _lib
+
+    checked = 0
     for t in [int(v) for v in g["record_ts"]]:
-        if precision == "tc" and _out_of_fp16_range(g, t):
-            continue
         rn, (ra, rl, rx, rx2) = _golden_noise(O, g, t, t)
         noise = InjectedNoise(rn.l_T, rn.x_T, ra, rl, rx, rx2, t_start=t)
         init = (torch.from_numpy(g[f"rec{t}_a_t"]), torch.from_numpy(g[f"rec{t}_x_t"]),
                 torch.from_numpy(g[f"rec{t}_l_t"]))
         a, x, l = model.sample_states(natoms, text, null, float(g["cond_scale"]), float(g["step_lr"]),
                                       noise=noise, t_start=t, t_stop=t - 1, init_state=init)
+        flags = model.last_flags.cpu()
+        if precision == "tc":
+            oor = _tc_out_of_range(sd, g[f"rec{t}_l_t"])
+            assert torch.equal((flags & _lib.FLAG_TC_RANGE) != 0, oor), f"t={t}: range flags {flags} vs {oor}"
+            if bool(oor.any()):
+                continue          # the library said so itself: these states are for exact mode
+        else:
+            assert int(flags.abs().sum()) == 0
+        checked += 1
         a_ref = g[f"rec{t}_a_next"]
         match = float((a.cpu().numpy() == a_ref).mean())
         if precision == "fp32":
             assert match == 1.0, f"t={t}: type mismatch"
         else:
-            assert match >= 0.9, f"t={t}: type match {match}"
+            assert match >= 0.99, f"t={t}: type match {match}"
         # the ancestral step multiplies the decoder's lattice error by c0 = 1/sqrt(alpha_t)
         # (= 100 at t = T, chemeleon.py:416-420); the per-step criterion is on the decoder outputs
         c0 = float(1.0 / torch.sqrt(schedules.beta_buffers(1000)["alphas"][t]))
         assert rel_err(l.cpu(), g[f"rec{t}_l_next"]) < tol * max(1.0, c0), f"t={t} lattice"
         d = np.abs((x.cpu().numpy() - g[f"rec{t}_x_next"] + 0.5) % 1.0 - 0.5).max()
         assert d < tol, f"t={t} coords {d}"
+    assert checked >= (2 if case == "c1_tamed_1000" else len(g["record_ts"]))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_forward_angstrom_cells(O, precision):
+    """CSPNetB200.forward against the REFERENCE CSPNet.forward (committed fixture) on hand-built
+    3..25 A sheared cells, n in {6, 20, 40, ragged}: the regime real sampling ends in."""
+    from chemeleon_b200.cspnet import CSPNetB200
+
+    for tag, sd, d in forward_golden_cases():
+        net = CSPNetB200(sd, precision=precision)
+        B = d["natoms"].shape[0]
+        bi = torch.arange(B).repeat_interleave(d["natoms"])
+        out = net(d["a"], d["x"], d["l"], d["natoms"], bi, t=O.time_embedding(d["t"], 128), text_embeds=d["text"])
+        assert int(net.engine.last_flags.abs().sum()) == 0, tag
+        errs = [rel_err(out.atom_types_out.cpu(), d["types"]), rel_err(out.lattice_out.cpu(), d["lattice"]),
+                rel_err(out.coords_out.cpu(), d["coords"])]
+        print(f"[{precision}/{tag}] forward rel err types {errs[0]:.2e} lattice {errs[1]:.2e} coords {errs[2]:.2e}")
+        assert max(errs) < TOL[precision], (tag, errs)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -272,8 +318,8 @@ def test_golden_decoder_outputs(O, precision):
         text, null = torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"]).expand(B, -1)
         cs = float(g["cond_scale"])
         for t in [int(v) for v in g["record_ts"]]:
-            if precision == "tc" and _out_of_fp16_range(g, t):
-                continue
+            if precision == "tc" and bool(_tc_out_of_range(sd, g[f"rec{t}_l_t"]).any()):
+                continue          # flagged by the library (asserted in test_golden_teacher_forced_steps)
             a, x, l = (torch.from_numpy(g[f"rec{t}_{k}"]) for k in ("a_t", "x_t", "l_t"))
             temb = O.time_embedding(torch.full((B,), t), 128)
             oc = net(a, x, l, nat, bi, t=temb, text_embeds=text)
@@ -283,11 +329,14 @@ def test_golden_decoder_outputs(O, precision):
                 assert rel_err(mix, g[f"rec{t}_{name}"]) < TOL[precision], (case, t, name)
 
 
-@pytest.mark.parametrize("precision,case", [(p, c) for p in PRECISIONS for c in ("c1_bounded_1000", "c1_tamed_1000")
-                                            if not (p == "tc" and c == "c1_tamed_1000")])
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", ["c1_bounded_1000", "ang_c1_1000", "c1_tamed_1000"])
 def test_golden_free_running_1000_steps(O, precision, case):
     """BASELINE config 1 (n_atoms=6, n_samples=3): the full 1000-step run with the
-    reference's own noise reproduces the reference's final structures (tamed heads)."""
+    reference's own noise reproduces the reference's final structures -- O(1) lattices
+    (c1_bounded), Angstrom-scale cells (ang_c1) and the exploding untamed lattice head
+    (c1_tamed: exact mode reproduces it; tensor-core mode must flag it)."""
+    from chemeleon_b200 import _lib
     from chemeleon_b200.sampler import ChemeleonB200, InjectedNoise
 
     g = load_golden(case)
@@ -298,6 +347,11 @@ def test_golden_free_running_1000_steps(O, precision, case):
     noise = InjectedNoise(rn.l_T, rn.x_T, ra, rl, rx, rx2, t_start=1000)
     a, x, l = model.sample_states(natoms, torch.from_numpy(g["text"]), torch.from_numpy(g["null_text"]),
                                   float(g["cond_scale"]), float(g["step_lr"]), noise=noise)
+    flags = model.last_flags.cpu()
+    if precision == "tc" and case == "c1_tamed_1000":
+        assert bool(((flags & _lib.FLAG_TC_RANGE) != 0).all()), flags     # cells of ~4000 A: out of range, and said so
+        return
+    assert int(flags.abs().sum()) == 0, flags
     match = float((a.cpu().numpy() == g["state0_a"]).mean())
     d = np.abs((x.cpu().numpy() - g["state0_x"] + 0.5) % 1.0 - 0.5).max()
     el = rel_err(l.cpu(), g["state0_l"])
@@ -305,7 +359,37 @@ def test_golden_free_running_1000_steps(O, precision, case):
     if precision == "fp32":
         assert match == 1.0 and d < 1e-3 and el < 1e-3
     else:
-        assert match >= 0.8 and el < 2e-2
+        assert match >= 0.99 and d < 1e-3 and el < 1e-3
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_batch_composition_invariance_at_benchmark_scale(precision):
+    """C3 scale (4096 x 20 atoms, 184 work items per CTA): three sampler steps of the full batch;
+    32 random crystals re-run ALONE (same global sample ids, so the same Philox noise) must give
+    the same structures -- types bit-equal, coordinates / lattice to 1e-5 (fp32 accumulation order of
+    the tensor-core tiles is not fixed, so this is not asserted bit-exact)."""
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.sampler import ChemeleonB200
+    from chemeleon_b200.weights import random_init_state_dict
+
+    B, n, steps = (4096, 20, 3) if precision == "tc" else (512, 20, 2)
+    cfg = SamplerConfig()
+    sd = random_init_state_dict(cfg, seed=0, head_scale=0.01, lattice_identity=True, lattice_gamma=0.5)
+    model = ChemeleonB200(sd, cfg, precision=precision)
+    g = torch.Generator().manual_seed(1)
+    text, null = torch.randn(B, cfg.text_dim, generator=g), torch.randn(1, cfg.text_dim, generator=g)
+    l_T, x_T = torch.randn(B, 3, 3, generator=g) * 4, torch.randn(B * n, 3, generator=g)
+    T = cfg.timesteps
+    a, x, l = model.sample_states([n] * B, text, null, seed=3, t_stop=T - steps, init_noise=(l_T, x_T))
+    pick = torch.randperm(B, generator=g)[:32].sort().values
+    nodes = (pick[:, None] * n + torch.arange(n)[None, :]).reshape(-1)
+    a2, x2, l2 = model.sample_states([n] * 32, text[pick], null, seed=3, t_stop=T - steps,
+                                     graph_gid=pick.tolist(), init_noise=(l_T[pick], x_T[nodes]))
+    assert torch.isfinite(x).all() and torch.isfinite(l).all()
+    assert torch.equal(a2.cpu(), a.cpu()[nodes])
+    dx = ((x2.cpu() - x.cpu()[nodes] + 0.5) % 1.0 - 0.5).abs().max()
+    assert float(dx) < 1e-5, float(dx)
+    assert rel_err(l2.cpu(), l.cpu()[pick]) < 1e-5
 
 
 def test_cuda_graph_equals_eager(O):
