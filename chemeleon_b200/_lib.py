@@ -22,7 +22,7 @@ PRECISION_TC_F16 = 1
 MODEL_EDGE_SINGLE_CTA = 1
 FLAG_NONFINITE = 1
 FLAG_TC_RANGE = 2
-TC_RANGE_LIMIT = 16384.0
+TC_RANGE_LIMIT = 96.0
 
 vp = C.c_void_p
 

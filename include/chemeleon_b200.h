@@ -147,11 +147,15 @@ typedef struct {
 
 /* per-crystal guard flags (cb2_state.flags, cb2_forward_io.flags) */
 #define CB2_FLAG_NONFINITE 1   /* the update produced NaN/Inf for this crystal */
-#define CB2_FLAG_TC_RANGE 2    /* tensor-core mode only: |W_ip vec(L L^T) + b1| > CB2_TC_RANGE_LIMIT, i.e. the edge
-                                * pre-activations leave the range of the fp16 GEMM2 operand (cells of several
-                                * hundred Angstrom; the reference itself discards cells > 60 A, evaluate.py:180).
-                                * Results for such a crystal are not covered by the 1e-3 tolerance: use exact mode. */
-#define CB2_TC_RANGE_LIMIT 16384.0f
+#define CB2_FLAG_TC_RANGE 2    /* tensor-core mode only: max |W_ip vec(L L^T) + b1| > CB2_TC_RANGE_LIMIT.  The edge
+                                * pre-activations and the aggregated edge features grow with this per-crystal term;
+                                * with fp16 operands (10-bit mantissa, like TF32) the decoder outputs stay within the
+                                * 1e-3 tolerance of the fp32 reference up to the limit (validated on reference
+                                * fixtures with cells of 3..40 Angstrom) and drift past it
+                                * beyond (1.2e-3 at 55 A cells; the reference itself discards cells > 60 A,
+                                * evaluate.py:180).  A flagged crystal is outside the validated range: re-run it in
+                                * exact mode. */
+#define CB2_TC_RANGE_LIMIT 96.0f
 
 /* ---- sampler state + one reverse-diffusion timestep (chemeleon.py:379-467) ---- */
 typedef struct {

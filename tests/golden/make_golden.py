@@ -115,14 +115,17 @@ def run_forward_cases(name="ang_forward"):
     model = ref_shim.build_reference_model(0)
     cfg = SamplerConfig()
     out = {}
-    cases = [("n6", [6, 6, 6]), ("n20", [20, 20]), ("n40", [40, 40]), ("ragged", [40, 33, 4, 1, 20])]
-    for ci, (tag, natoms) in enumerate(cases):
+    # (tag, natoms, scale of the 3..25 A cell lengths): the *x cases reach 40 A, the upper end of the
+    # range the tensor-core path is validated for (lattice term just below CB2_TC_RANGE_LIMIT)
+    cases = [("n6", [6, 6, 6], 1.0), ("n20", [20, 20], 1.0), ("n40", [40, 40], 1.0), ("ragged", [40, 33, 4, 1, 20], 1.0),
+             ("n20x", [20, 20], 1.7), ("n6x", [6, 6, 6], 1.7)]
+    for ci, (tag, natoms, scale) in enumerate(cases):
         sd = random_init_state_dict(cfg, seed=20 + ci)
         res = model.load_state_dict(sd, strict=False)
         assert not [k for k in res.missing_keys if k.startswith("decoder.")], res
         B, N = len(natoms), sum(natoms)
         g = torch.Generator().manual_seed(100 + ci)
-        abc = 3.0 + 22.0 * torch.rand(B, 3, generator=g)                      # 3..25 A
+        abc = (3.0 + 22.0 * torch.rand(B, 3, generator=g)) * scale            # 3..25 A (x scale)
         l = torch.diag_embed(abc)
         shear = (torch.rand(B, 3, 3, generator=g) - 0.5) * 0.6 * abc[:, :, None]   # up to +-30 % of the length
         l = l + shear * (1 - torch.eye(3))
