@@ -48,6 +48,7 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
 int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const float *bias, float *C,
                      int64_t ldc, int64_t M, int K, int silu, void *workspace, size_t workspace_bytes, cudaStream_t st);
 int debug_edge_timeline(long long *out96);
+int debug_edge2_timeline(long long *out96x3);
 int tc_edge_layer(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P,
                   const float *cg, __half *agg16, int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
 
@@ -228,6 +229,7 @@ int cb2_validity_filter(const int64_t *atom_types, const float *frac_coords, con
 
 /* development aid (not part of the documented ABI): clock64 timeline of the edge kernel's CTA 0 */
 int cb2_debug_edge_timeline(long long *out96) { return debug_edge_timeline(out96); }
+int cb2_debug_edge2_timeline(long long *out96x3) { return debug_edge2_timeline(out96x3); }
 
 int cb2_check_device(int device) {
   cudaDeviceProp prop;

@@ -206,6 +206,9 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ... with the B operand MN-major (the contiguous 16 bytes run along N)
+__host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
+
 // D[tmem] (+)= A[smem] B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -275,5 +278,66 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+}  // namespace ptx
+}  // namespace cb2
+
+// ---- CTA pairs: cta_group::2 (one MMA spans two SMs, M = 256) + tensor-map TMA --------------------
+// All tcgen05 instructions of a kernel must use the same cta_group: a kernel that issues the
+// pair MMA allocates / commits / deallocates with these variants only.
+namespace cb2 {
+namespace ptx {
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A B^T with M = 256: rows 0..127 of A / D live in the even CTA, rows
+// 128..255 in the odd one; each CTA supplies half of B's N rows.  Issued by ONE thread of the even CTA;
+// the descriptors address the same shared-memory offsets in both CTAs.
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of cta_mask once all MMAs issued so far by this
+// thread have completed
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+// Tensor-map TMA (UTMALDG), 3-D box global -> shared memory of the executing CTA; the transaction
+// bytes are credited to `bar`, which may live in the PEER CTA of the pair (cta_group::2): both CTAs'
+// loads complete on the even CTA's barrier, where the single MMA-issuing thread waits.
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst_smem, const void *tmap, int c0, int c1, int c2,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// mbarrier.arrive on a barrier of this CTA with cluster-scope release (its waiter may be woken by
+// arrivals from both CTAs and must see this thread's remote stores as well)
+// arrive (CTA-scope release) on an mbarrier of another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 }  // namespace ptx
 }  // namespace cb2

@@ -19,7 +19,7 @@
 //   warps 0-15: worker warp w owns TMEM lane quarter w%4 of unit w/4 (init, E1, E2) and, as
 //               member of embedding group w/4, the edge row (w%4)*32+lane of every 4th K chunk
 //   warp 16   : MMA issue (one lane), TMEM alloc        warp 17: weight loader (bulk copies)
-#include "cb2_tc.cuh"
+#include "cb2_tc_edge_epi.cuh"
 
 namespace cb2 {
 
@@ -47,19 +47,11 @@ constexpr int TE_NCH2 = 4;                      // per output unit: 4 stages of 
 #define CB2_TE_DEFER 4
 #endif
 constexpr int TE_DEFER = CB2_TE_DEFER;                     // GEMM1 chunks issued for units 0..2 before unit 3 is clear (<= 5 W stages)
-constexpr uint32_t TE_PAD = 0xFFFFFFFFu;        // off_i of a padding row
 static_assert(TE_SMEM <= 232448, "shared memory budget");
 static_assert(TE_NCH2 >= TE_NISSUE, "every issuer must own a stage of every output unit");
 
 // single-thread roles on the critical path poll their barriers (see mbar_wait_spin)
 #define MBAR_WAIT_CRIT mbar_wait_spin
-#ifdef CB2_SPIN_WORKERS
-#define MBAR_WAIT_WORKER mbar_wait_spin
-#else
-#define MBAR_WAIT_WORKER mbar_wait
-#endif
-
-__host__ __device__ constexpr uint32_t idesc_b_mn(uint32_t d) { return d | (1u << 16); }
 
 __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
   uint32_t v;
@@ -68,188 +60,6 @@ __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
 }
 __device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-// ---- E2 body: mean over the n edges of each segment of SiLU(U + b2) for one TMEM unit ----
-// Segment boundaries are compile-time for N > 0 (no branches in the running sum); N == 0 is
-// the generic runtime-n version used for segment lengths without a specialisation.
-// Output row r of channel c lives at out[(r / 128) * ld_agg.hi + (r % 128) * ld_agg.lo]: row-major
-// (hi = 128 ld, lo = ld) or the row-panel layout of the GEMM A operands (hi = 128 kt, lo = 8).
-struct AggStride { int64_t hi; int lo; uint32_t row0; };   // row0: added to the table's node row (variant base)
-__device__ __forceinline__ void e2_store(const uint32_t *t_oi, int seg0, __half *out, AggStride ld_agg, float mean) {
-  const uint32_t o = t_oi[seg0];
-  if (o != TE_PAD) {
-    const uint32_t r = (o >> 10) + ld_agg.row0;
-    out[(int64_t)(r >> 7) * ld_agg.hi + (int)(r & 127) * ld_agg.lo] = __float2half_rn(fminf(fmaxf(mean, -65504.f), 65504.f));
-  }
-}
-
-template <int N>
-__device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
-                                     AggStride ld_agg) {
-  const int n = N > 0 ? N : n_rt;
-  const float inv_n = 1.0f / (float)n;
-  float sum = 0.f;
-  int cnt = 0, seg0 = 0;
-  uint32_t accA[32], accB[32];
-  tmem_ld32(taddr, accA);
-#pragma unroll
-  for (int cb = 0; cb < 4; cb++) {
-    tmem_ld_wait();
-    uint32_t (&acc)[32] = (cb & 1) ? accB : accA;
-    uint32_t (&nxt)[32] = (cb & 1) ? accA : accB;
-    if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);   // next chunk's TMEM read overlaps this chunk's math
-    float t[32];
-#pragma unroll
-    // fp32 tanh here (one MUFU op per element): measured as fast as the paired fp16 form -- E2 of a
-    // unit runs on four warps and is latency-bound -- and the mean is taken over unrounded values
-    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      sum += t[j];
-      if (N > 0) {
-        if ((cb * 32 + j + 1) % (N > 0 ? N : 1) == 0) {
-          e2_store(t_oi, cb * 32 + j + 1 - N, out, ld_agg, sum * inv_n);
-          sum = 0.f;
-        }
-      } else if (++cnt == n) {
-        e2_store(t_oi, seg0, out, ld_agg, sum * inv_n);
-        sum = 0.f;
-        cnt = 0;
-        seg0 += n;
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
-                                            AggStride ld_agg) {
-  switch (n) {
-#define CB2_E2_CASE(N) case N: e2_unit<N>(n, taddr, bias, t_oi, out, ld_agg); break;
-    CB2_E2_CASE(1) CB2_E2_CASE(2) CB2_E2_CASE(3) CB2_E2_CASE(4) CB2_E2_CASE(5) CB2_E2_CASE(6) CB2_E2_CASE(7)
-    CB2_E2_CASE(8) CB2_E2_CASE(9) CB2_E2_CASE(10) CB2_E2_CASE(11) CB2_E2_CASE(12) CB2_E2_CASE(13) CB2_E2_CASE(14)
-    CB2_E2_CASE(15) CB2_E2_CASE(16) CB2_E2_CASE(17) CB2_E2_CASE(18) CB2_E2_CASE(19) CB2_E2_CASE(20) CB2_E2_CASE(21)
-    CB2_E2_CASE(22) CB2_E2_CASE(23) CB2_E2_CASE(24) CB2_E2_CASE(25) CB2_E2_CASE(26) CB2_E2_CASE(27) CB2_E2_CASE(28)
-    CB2_E2_CASE(29) CB2_E2_CASE(30) CB2_E2_CASE(31) CB2_E2_CASE(32) CB2_E2_CASE(33) CB2_E2_CASE(34) CB2_E2_CASE(35)
-    CB2_E2_CASE(36) CB2_E2_CASE(37) CB2_E2_CASE(38) CB2_E2_CASE(39) CB2_E2_CASE(40)
-#undef CB2_E2_CASE
-    default: e2_unit<0>(n, taddr, bias, t_oi, out, ld_agg); break;
-  }
-}
-
-// ---- E1 body: a1[c][e] = SiLU(U[c][e] + P_i[i(e)][c] + P_j[j(e)][c]) for one lane quarter of a unit ----
-// The hoisted node terms are gathered thread = channel (128 B per warp and node) BEFORE the wait
-// on the GEMM1 accumulator, so their latency is off the critical path.  N > 0: the tile's segment
-// structure is compile-time, each thread loads P_i once per segment and the N rows of P_j once
-// per crystal (they repeat for every segment of the same crystal).  N == 0: generic version, two
-// gathers per edge.
-// The per-crystal lattice term cg[g][c] (fp32, O(10..100) for Angstrom-scale cells) is added here in
-// fp32 -- it is never folded into the fp16 P rows, whose O(1) node signal it would swamp.
-struct E1Cg { const float *cgc; const int32_t *n2g; uint32_t vbase; };   // cgc = cg + channel (NULL: no term)
-__device__ __forceinline__ float e1_cg(const E1Cg &k, uint32_t oi) {
-  return k.cgc ? __ldg(k.cgc + (size_t)__ldg(k.n2g + ((oi >> 10) - k.vbase)) * H) : 0.f;
-}
-
-template <int N>
-__device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, E1Cg cgk, const uint32_t *t_oi, const uint32_t *t_oj,
-                                     uint8_t *a1_dst, uint32_t acc1_full, uint32_t parity) {
-  if constexpr (N == 0) {
-    const uint4 *ti = reinterpret_cast<const uint4 *>(t_oi);
-    const uint4 *tj = reinterpret_cast<const uint4 *>(t_oj);
-    MBAR_WAIT_WORKER(acc1_full, parity);
-    tc_fence_after_sync();
-#pragma unroll 1
-    for (int cb = 0; cb < 4; cb++) {
-      uint32_t acc[32];
-      tmem_ld32(taddr + cb * 32, acc);
-      float pv[32];
-#pragma unroll
-      for (int j4 = 0; j4 < 8; j4++) {
-        const uint4 oi = ti[cb * 8 + j4], oj = tj[cb * 8 + j4];
-        const uint32_t ois[4] = {oi.x, oi.y, oi.z, oi.w};
-        const uint32_t ojs[4] = {oj.x, oj.y, oj.z, oj.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          pv[j4 * 4 + k] = ois[k] == TE_PAD ? 0.f : __half2float(Pc[ois[k]]) + e1_cg(cgk, ois[k]) + __half2float(Pc[ojs[k]]);
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-          w[e] = silu2_half(__uint_as_float(acc[8 * p + 2 * e]) + pv[8 * p + 2 * e],
-                            __uint_as_float(acc[8 * p + 2 * e + 1]) + pv[8 * p + 2 * e + 1]);
-        *reinterpret_cast<uint4 *>(a1_dst + (cb * 4 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  } else {
-    constexpr int S = 128 / N;
-    float piv[S];
-#pragma unroll
-    for (int sgm = 0; sgm < S; sgm++) {
-      const uint32_t oi = t_oi[sgm * N];
-      piv[sgm] = oi == TE_PAD ? 0.f : __half2float(Pc[oi]) + e1_cg(cgk, oi);
-    }
-    float pj[N];
-    uint32_t cur = t_oj[0];
-#pragma unroll
-    for (int k = 0; k < N; k++) pj[k] = __half2float(Pc[cur + (uint32_t)k * (uint32_t)H2]);
-    MBAR_WAIT_WORKER(acc1_full, parity);
-    tc_fence_after_sync();
-    // 16-column TMEM loads, double-buffered: the load of block hb+1 is in flight while block hb
-    // goes through the SiLU (register budget: 2 x 16 accumulators + P_i / P_j values)
-    uint32_t accA[16], accB[16];
-    tmem_ld16(taddr, accA);
-#pragma unroll
-    for (int hb = 0; hb < 8; hb++) {
-      tmem_ld_wait();
-      uint32_t (&acc)[16] = (hb & 1) ? accB : accA;
-      uint32_t (&nxt)[16] = (hb & 1) ? accA : accB;
-      if (hb < 7) tmem_ld16(taddr + (hb + 1) * 16, nxt);
-      float x[16];
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int e = hb * 16 + j;
-        x[j] = __uint_as_float(acc[j]);
-        if (e < S * N) {
-          if (e % N == 0 && e > 0) {            // segment start: same crystal as before?
-            const uint32_t oj0 = t_oj[e];
-            if (oj0 != cur) {
-              cur = oj0;
-#pragma unroll
-              for (int k = 0; k < N; k++) pj[k] = __half2float(Pc[cur + (uint32_t)k * (uint32_t)H2]);
-            }
-          }
-          x[j] += piv[e / N] + pj[e % N];
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < 2; p++) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) w[e] = silu2_half(x[8 * p + 2 * e], x[8 * p + 2 * e + 1]);
-        *reinterpret_cast<uint4 *>(a1_dst + (hb * 2 + p) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half *Pc, E1Cg cgk, const uint32_t *t_oi,
-                                            const uint32_t *t_oj, uint8_t *a1_dst, uint32_t acc1_full,
-                                            uint32_t parity) {
-  switch (n) {
-#define CB2_E1_CASE(N) case N: e1_unit<N>(taddr, Pc, cgk, t_oi, t_oj, a1_dst, acc1_full, parity); break;
-    CB2_E1_CASE(4) CB2_E1_CASE(5) CB2_E1_CASE(6) CB2_E1_CASE(7)
-    CB2_E1_CASE(8) CB2_E1_CASE(9) CB2_E1_CASE(10) CB2_E1_CASE(11) CB2_E1_CASE(12) CB2_E1_CASE(13)
-    CB2_E1_CASE(14) CB2_E1_CASE(15) CB2_E1_CASE(16) CB2_E1_CASE(17) CB2_E1_CASE(18) CB2_E1_CASE(19)
-    CB2_E1_CASE(20) CB2_E1_CASE(21) CB2_E1_CASE(22) CB2_E1_CASE(23) CB2_E1_CASE(24) CB2_E1_CASE(25)
-    CB2_E1_CASE(26) CB2_E1_CASE(27) CB2_E1_CASE(28) CB2_E1_CASE(29) CB2_E1_CASE(30) CB2_E1_CASE(31)
-    CB2_E1_CASE(32) CB2_E1_CASE(33) CB2_E1_CASE(34) CB2_E1_CASE(35) CB2_E1_CASE(36) CB2_E1_CASE(37)
-    CB2_E1_CASE(38) CB2_E1_CASE(39) CB2_E1_CASE(40)
-#undef CB2_E1_CASE
-    default: e1_unit<0>(taddr, Pc, cgk, t_oi, t_oj, a1_dst, acc1_full, parity); break;
-  }
 }
 
 // Note on mbarrier parities: a wait only compares one parity bit, so a thread that asks for phase
@@ -449,7 +259,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
     const AggStride agg_ld = g.agg_kt > 0 ? AggStride{(int64_t)128 * g.agg_kt, 8, 0u}
                                           : AggStride{(int64_t)128 * g.ld_agg, (int)g.ld_agg, 0u};
-    uint8_t *a1_dst = smem + (size_t)(c / 8) * 2048 + (c % 8) * 16;
+    const A1Dst a1_dst{sbase + (uint32_t)((c / 8) * 2048 + (c % 8) * 16), 0u};
 
     // The (i, j) node ids of this thread's edge row are fetched one item ahead (fetch_rows); the
     // tile tables (group 0 writes them) and the fractional-coordinate difference follow half an
@@ -564,7 +374,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
       if (has_next) publish_rows(next, buf ^ 1, dlt_next);
       // ---- E1: a1 = SiLU(U + P_i + P_j), thread = channel, MN-major fp16 operand of GEMM2 ----
       if (tid == 0) TE_STAMP(8);
-      const E1Cg cgk{g.cg ? g.cg + c : nullptr, g.node2graph, (uint32_t)(item / g.n_tiles) * (uint32_t)g.N};
+      const E1Cg cgk{g.cg ? g.cg + c : nullptr, g.node2graph, (uint32_t)(item / g.n_tiles) * (uint32_t)g.N, nullptr};
       e1_dispatch(n, taddr, Pc, cgk, t_oi, t_oi + 128, a1_dst, acc1_full, it & 1);
       if (tid == 0) TE_STAMP(9);
       {  // pre-load the unit with b2: every GEMM2 MMA accumulates, so the issuers need no ordering
@@ -606,9 +416,13 @@ int debug_edge_timeline(long long *out96) {
   return CB2_OK;
 }
 
+int launch_tc_edge2(const TcEdgeArgs &a, int n_sm, cudaStream_t st);   // cb2_tc_edge2.cu
+
 int launch_tc_edge(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {
   const int n_items = a.n_tiles * a.V;
   if (n_items == 0) return CB2_OK;
+  // both CFG variants: the CTA-pair kernel shares the sinusoid GEMM between them (default)
+  if (a.V == 2 && !a.single_cta && n_sm >= 2) return launch_tc_edge2(a, n_sm, st);
   if ((uint64_t)a.V * (uint64_t)a.N * (uint64_t)H2 >= (1ull << 32))
     return fail(CB2_ERR_UNSUPPORTED, "tensor-core edge kernel: V*N*1024 must fit 32 bits (shard the batch)");
   // per-device function attribute: set on every launch (cheap, legal during stream capture)

@@ -35,17 +35,36 @@ print(f"edge layer B={B} n={n}: {ms:.3f} ms/launch  {fl/ms/1e9:.1f} TFLOP/s  til
 if os.environ.get("CB2_TIMELINE"):
     import numpy as np
     buf = (C.c_longlong * 288)()
-    eng.lib.cb2_debug_edge_timeline.argtypes = [C.c_void_p]
-    eng.lib.cb2_debug_edge_timeline(buf)
+    pair = not os.environ.get("CB2_SINGLE_CTA")
+    fn = eng.lib.cb2_debug_edge2_timeline if pair else eng.lib.cb2_debug_edge_timeline
+    fn.argtypes = [C.c_void_p]
+    fn(buf)
     a = np.array(buf[:]).reshape(3, 96)
-    names = {0: "mma:top", 1: "mma:acc_init ok", 2: "mma:G1 issued", 3: "mma:a1_ready ok", 4: "mma:G2(0) issued", 5: "G2(1)", 6: "G2(2)", 7: "G2(3)",
-             8: "w0:emb done", 9: "w0:acc1_full ok", 10: "w0:E1 done", 11: "u0:acc2_full ok", 12: "u0:E2 done", 13: "u0:init done",
-             15: "u1:acc2 ok", 16: "u1:E2 done", 17: "u1:init done", 19: "u2:acc2 ok", 20: "u2:E2 done", 21: "u2:init done",
-             23: "u3:acc2 ok", 24: "u3:E2 done", 25: "u3:init done"}
-    for itx in range(3):
-        base = a[itx, 0]
-        ev = sorted((int(a[itx, k] - base), names[k]) for k in names if a[itx, k] != 0)
-        print("item", itx + 1, " | ".join(f"{n}@{t}" for t, n in ev))
-        print("   producer g0 (slot free, chunk published):", [int(a[itx, 32 + k] - base) for k in range(12)])
-        print("   mma chunk start times:", [int(a[itx, 48 + k] - base) for k in range(24)])
-
+    if pair:
+        names = {0: "mma:top", 1: "mma:x_free ok", 2: "mma:G1 issued", 3: "mma:a1_ready ok", 4: "mma:o0_ready ok"}
+        for gq in range(4):
+            for k, nm in enumerate(["top", "emb12 done", "E1 done", "a1 arrived", "emb0' done", "o_full ok", "E2 done", "refilled"]):
+                names[8 + 8 * gq + k] = f"g{gq}:{nm}"
+        for itx in range(3):
+            base = a[itx, 0]
+            ev = sorted((int(a[itx, k] - base), names[k]) for k in names if a[itx, k] != 0)
+            print("tile", itx + 1, " | ".join(f"{n}@{t}" for t, n in ev))
+            print("   G1 chunk issue times:", [int(a[itx, 48 + k] - base) for k in range(24)])
+            print("   G2 stage issue times:", [int(a[itx, 72 + k] - base) for k in range(16)])
+            print("   issuer chunk 12: before waits, a_full ok, (w_full ok = chunk time), MMAs issued, commits issued:",
+                  [int(a[itx, k] - base) for k in (88, 89, 48 + 12, 90, 91)])
+            print("   E1 tail g0 (local a1) / g1 (remote a1): after bar, after fill, after fence.proxy:",
+                  [int(a[itx, k] - base) for k in (40, 41, 42)], [int(a[itx, k] - base) for k in (44, 45, 46)])
+            print("   E1 (thread 0): entry (P loads issued), x_full ok, first 16 columns done, 64 columns done:",
+                  [int(a[itx, 32 + k] - base) for k in range(4)], "tmem_ld issued, first tmem data:", [int(a[itx, 32 + k] - base) for k in (4, 5)])
+            print("   loader stage 16 (for chunk 16): before w_empty wait, w_empty ok, TMA issued:",
+                  [int(a[itx, k] - base) for k in (92, 93, 94)])
+    else:
+        names = {0: "mma:top", 1: "mma:acc_init ok", 2: "mma:G1 issued", 3: "mma:a1_ready ok", 4: "mma:G2(0) issued", 5: "G2(1)", 6: "G2(2)", 7: "G2(3)",
+                 8: "w0:emb done", 9: "w0:acc1_full ok", 10: "w0:E1 done", 11: "u0:acc2_full ok", 12: "u0:E2 done", 13: "u0:init done",
+                 15: "u1:acc2 ok", 16: "u1:E2 done", 17: "u1:init done", 19: "u2:acc2 ok", 20: "u2:E2 done", 21: "u2:init done",
+                 23: "u3:acc2 ok", 24: "u3:E2 done", 25: "u3:init done"}
+        for itx in range(3):
+            base = a[itx, 0]
+            ev = sorted((int(a[itx, k] - base), names[k]) for k in names if a[itx, k] != 0)
+            print("item", itx + 1, " | ".join(f"{n}@{t}" for t, n in ev))

@@ -76,3 +76,36 @@ def test_edge_layer_tc_vs_fp32(natoms, V, cg_scale):
     err = rel_err(agg16.float().cpu(), agg32.cpu())
     print(f"edge layer tc vs fp32: rel err {err:.2e}")
     assert err < 2e-3
+
+
+@pytest.mark.parametrize("natoms", [[20] * 300, [4, 7, 5, 1, 40, 33], [6, 6, 6], [40] * 37 + [13] * 5 + [64, 3]])
+def test_edge_pair_kernel_matches_single_cta_kernel(natoms):
+    """V = 2: the CTA-pair kernel (cta_group::2, sinusoid GEMM shared by the CFG variants, a1 halves
+    exchanged through distributed shared memory, tensor-map TMA) gives the aggregates of the one-CTA
+    kernel run per variant (selected with cb2_model.flags); only the fp32 accumulation order differs."""
+    from chemeleon_b200 import _lib
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.engine import DecoderEngine
+    from chemeleon_b200.topology import BatchTopology
+    from chemeleon_b200.weights import random_init_state_dict
+
+    cfg = SamplerConfig(num_layers=1)
+    eng = DecoderEngine(random_init_state_dict(cfg, seed=4), cfg, precision="tc")
+    topo = BatchTopology(natoms, 2, "cuda", exact=False, tensor_core=True)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(topo.N, 3, generator=g) * 2 - 0.5).cuda()
+    P = torch.randn(2 * topo.N, 1024, generator=g).cuda().half()
+    cg = (torch.randn(topo.B, 512, generator=g) * 5).cuda()
+    outs = []
+    for flags in (_lib.MODEL_EDGE_SINGLE_CTA, 0):
+        eng.model.flags = flags
+        agg = torch.full((2 * topo.N, 512), float("nan"), device="cuda", dtype=torch.float16)
+        for _ in range(2):          # twice: the second launch starts from whatever the first left in TMEM / smem
+            _lib.check(eng.lib.cb2_edge_layer(C.byref(eng.model), 0, topo.byref(), x.data_ptr(), P.data_ptr(),
+                                              cg.data_ptr(), agg.data_ptr(), 512, 1, None, 0, _stream()), "edge")
+        torch.cuda.synchronize()
+        assert torch.isfinite(agg).all()
+        outs.append(agg.float().cpu())
+    err = rel_err(outs[1], outs[0])
+    print(f"pair vs single-CTA edge kernel: rel err {err:.2e}")
+    assert err < 1e-3   # both round a1 / agg to fp16; a last-bit flip of an fp16 output is 5e-4 of its value
