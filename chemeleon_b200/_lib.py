@@ -73,12 +73,17 @@ class State(C.Structure):
 
 class StepArgs(C.Structure):
     _fields_ = [
-        ("coef", vp), ("text_part", vp),
+        ("coef", vp), ("text_part", vp), ("text_row", vp),
         ("cond_scale", C.c_float), ("timesteps", C.c_int32), ("precision", C.c_int32),
         ("noise_mode", C.c_int32), ("t_start", C.c_int32),
         ("rand_a", vp), ("rand_l", vp), ("rand_x", vp), ("rand_x2", vp),
         ("seed", C.c_uint64), ("seed_dev", vp), ("graph_gid", vp),
     ]
+
+
+class TextTail(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("text_dim", C.c_int32)] + [(n, vp) for n in (
+        "w1", "b1", "ln_g", "ln_b", "w2", "b2", "null_embeds", "w_text", "b_cond")]
 
 
 EXPORTS = {
@@ -89,6 +94,8 @@ EXPORTS = {
     "cb2_workspace_bytes": (C.c_size_t, [C.POINTER(Model), C.POINTER(Batch), C.c_int]),
     "cb2_embed_nodes": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), vp, vp, vp]),
     "cb2_film_cond": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), vp, vp, vp, vp]),
+    "cb2_text_condition": (C.c_int, [C.POINTER(TextTail), vp, C.c_int32, vp, vp, C.c_size_t, vp]),
+    "cb2_text_condition_workspace_bytes": (C.c_size_t, [C.POINTER(TextTail), C.c_int32]),
     "cb2_linear_f32": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, vp]),
     "cb2_linear_tc": (C.c_int, [vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32,

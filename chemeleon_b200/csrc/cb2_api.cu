@@ -19,8 +19,9 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 // launchers from the other translation units
 int launch_embed(const int64_t *a, const float *emb, float *h, int N, int V, cudaStream_t st);
-int launch_film_cond(const float *time_table, const float *text_part, const int32_t *t_dev, float *out,
-                     int64_t rows, cudaStream_t st);
+int launch_film_cond(const float *time_table, const float *text_part, const int32_t *text_row, const int32_t *t_dev,
+                     float *out, int64_t rows, cudaStream_t st);
+int launch_ln_gelu(float *x, const float *g, const float *b, int width, int64_t rows, cudaStream_t st);
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
@@ -263,8 +264,46 @@ int cb2_film_cond(const cb2_model *m, const cb2_batch *b, const float *text_part
   if (!b || !text_part || !film_cond) return fail(CB2_ERR_BAD_ARG, "film_cond: null argument");
   if (t_dev != nullptr && m->film_time_table == nullptr)
     return fail(CB2_ERR_BAD_ARG, "film_cond: t_dev given but the model has no film_time_table");
-  return launch_film_cond(t_dev ? m->film_time_table : nullptr, text_part, t_dev, film_cond,
+  return launch_film_cond(t_dev ? m->film_time_table : nullptr, text_part, nullptr, t_dev, film_cond,
                           (int64_t)b->n_variants * b->n_graphs, (cudaStream_t)stream);
+}
+
+size_t cb2_text_condition_workspace_bytes(const cb2_text_tail *t, int32_t n_prompts) {
+  if (!t || n_prompts < 0) return 0;
+  const size_t R = (size_t)n_prompts + 1;
+  return ((R * t->embed_dim * sizeof(float) + 255) & ~size_t(255)) * 2 + ((R * t->text_dim * sizeof(float) + 255) & ~size_t(255));
+}
+
+int cb2_text_condition(const cb2_text_tail *t, const float *enc, int32_t n_prompts, float *text_part, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  if (!t || !text_part || (n_prompts > 0 && !enc) || n_prompts < 0) return fail(CB2_ERR_BAD_ARG, "text_condition: null argument");
+  if (!t->w1 || !t->b1 || !t->ln_g || !t->ln_b || !t->w2 || !t->b2 || !t->null_embeds || !t->w_text || !t->b_cond)
+    return fail(CB2_ERR_BAD_ARG, "text_condition: cb2_text_tail has a null weight");
+  const int E = t->embed_dim, D = t->text_dim;
+  if (E % 32 != 0 || D % 16 != 0 || E <= 0 || D <= 0)
+    return fail(CB2_ERR_UNSUPPORTED, "text_condition: embed_dim % 32 and text_dim % 16 must be 0");
+  const int64_t R = (int64_t)n_prompts + 1;
+  Arena a(workspace, workspace_bytes, false);
+  float *x = a.take<float>((size_t)R * E);      // encoder rows, then the learned null embedding
+  float *y = a.take<float>((size_t)R * E);
+  float *z = a.take<float>((size_t)R * D);
+  if (!workspace || !a.ok()) return fail(CB2_ERR_WORKSPACE, "text_condition: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_prompts > 0)
+    CB2_CUDA_OK(cudaMemcpyAsync(x, enc, (size_t)n_prompts * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CB2_CUDA_OK(cudaMemcpyAsync(x + (size_t)n_prompts * E, t->null_embeds, (size_t)E * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  GemmEpilogue e1;
+  e1.bias = t->b1;
+  CB2_TRY(launch_sgemm_nt(x, E, t->w1, y, E, R, E, E, e1, st));            // text_emb.0
+  CB2_TRY(launch_ln_gelu(y, t->ln_g, t->ln_b, E, R, st));                   // text_emb.1, text_emb.2
+  GemmEpilogue e2;
+  e2.bias = t->b2;
+  CB2_TRY(launch_sgemm_nt(y, E, t->w2, z, D, R, D, E, e2, st));            // text_emb.3 -> [R, text_dim]
+  GemmEpilogue e3;
+  e3.bias = t->b_cond;
+  CB2_TRY(launch_sgemm_nt(z, D, t->w_text, text_part, H2, R, H2, D, e3, st));   // text half of FilmLayer.mlp_cond
+  return CB2_OK;
 }
 
 int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bias, float *C, int64_t ldc,
@@ -346,7 +385,7 @@ int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const
   carve_forward(ar, b, m->n_layers, a->precision, fw);
   carve_step(ar, b, sw);
   if (!workspace || !ar.ok()) return fail(CB2_ERR_WORKSPACE, "workspace too small: call cb2_workspace_bytes()");
-  CB2_TRY(launch_film_cond(m->film_time_table, a->text_part, s->t_dev, sw.film_cond,
+  CB2_TRY(launch_film_cond(m->film_time_table, a->text_part, a->text_row, s->t_dev, sw.film_cond,
                            (int64_t)b->n_variants * b->n_graphs, st));
   cb2_forward_io io{};
   io.atom_types = s->atom_types;

@@ -34,21 +34,24 @@ int launch_embed(const int64_t *a, const float *emb, float *h, int N, int V, cud
 // ---------------------------------------------------------------------------
 // FiLM conditioning: cond[r] = SiLU(time_table[t] + text_part[r])   (cspnet.py:70-73,80-81)
 // ---------------------------------------------------------------------------
+// text_row (optional): crystal r uses row text_row[r] of text_part, so that crystals with the same
+// prompt share one row (and all null rows are one row)
 __global__ void k_film_cond(const float *__restrict__ time_table, const float *__restrict__ text_part,
-                            const int32_t *__restrict__ t_dev, float *__restrict__ out, int64_t rows) {
+                            const int32_t *__restrict__ text_row, const int32_t *__restrict__ t_dev,
+                            float *__restrict__ out, int64_t rows) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * H2) return;
   int c = (int)(idx % H2);
-  float v = text_part[idx];
+  float v = text_row ? text_part[(int64_t)text_row[idx / H2] * H2 + c] : text_part[idx];
   if (time_table != nullptr) v += time_table[(int64_t)(*t_dev) * H2 + c];
   out[idx] = silu_exact(v);
 }
 
-int launch_film_cond(const float *time_table, const float *text_part, const int32_t *t_dev, float *out,
-                     int64_t rows, cudaStream_t st) {
+int launch_film_cond(const float *time_table, const float *text_part, const int32_t *text_row, const int32_t *t_dev,
+                     float *out, int64_t rows, cudaStream_t st) {
   int64_t total = rows * H2;
   if (total == 0) return CB2_OK;
-  k_film_cond<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(time_table, text_part, t_dev, out, rows);
+  k_film_cond<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(time_table, text_part, text_row, t_dev, out, rows);
   CB2_LAUNCH_OK("k_film_cond");
   return CB2_OK;
 }
@@ -494,6 +497,40 @@ int launch_to_half(const float *x, __half *y, int64_t n, cudaStream_t st) {
   if (n == 0) return CB2_OK;
   k_to_half<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(x, y, n / 4);
   CB2_LAUNCH_OK("k_to_half");
+  return CB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Text-conditioning tail (TextEncoder.get_text_embeds after the language model,
+// text_encoder/text_encoder.py:40-45,186-205): x -> Linear -> LayerNorm -> GELU (exact, erf) -> Linear.
+// This kernel is the LayerNorm + GELU between the two fp32 GEMMs; one warp per row, any width % 32 == 0.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ln_gelu(float *__restrict__ x, const float *__restrict__ g,
+                                                 const float *__restrict__ b, int width, int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float *p = x + row * width;
+  float s = 0.f;
+  for (int c = lane; c < width; c += 32) s += p[c];
+  const float mean = warp_sum(s) / (float)width;
+  float s2 = 0.f;
+  for (int c = lane; c < width; c += 32) {
+    const float d = p[c] - mean;
+    s2 += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(s2) / (float)width + 1e-5f);
+  for (int c = lane; c < width; c += 32) {
+    const float v = (p[c] - mean) * rstd * g[c] + b[c];
+    p[c] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  }
+}
+
+int launch_ln_gelu(float *x, const float *g, const float *b, int width, int64_t rows, cudaStream_t st) {
+  if (rows == 0) return CB2_OK;
+  if (width % 32 != 0) return fail(CB2_ERR_BAD_ARG, "ln_gelu: width must be a multiple of 32");
+  k_ln_gelu<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, b, width, rows);
+  CB2_LAUNCH_OK("k_ln_gelu");
   return CB2_OK;
 }
 

@@ -104,10 +104,16 @@ def prepare_sharded_run(model, plan: ShardPlan, text_embeds: Optional[torch.Tens
         l_T, x_T = model.initial_noise(plan.B, plan.N, seed)   # global order on every rank
         nodes = torch.from_numpy(plan.my_nodes).to(x_T.device)
         gi = torch.tensor(plan.mine, dtype=torch.int64, device=x_T.device)
-        te = text_embeds[gi.to(text_embeds.device)] if text_embeds is not None else None
-        ne = null_text_embeds
-        if ne is not None and ne.shape[0] == plan.B and plan.B != 1:
-            ne = ne[gi.to(ne.device)]
+        from .sampler import TextCondition
+
+        if isinstance(text_embeds, TextCondition):   # shared FiLM rows + the row of every (variant, crystal)
+            ro = text_embeds.row_of.to(x_T.device)
+            te, ne = TextCondition(text_embeds.rows, torch.cat([ro[gi], ro[plan.B + gi]])), None
+        else:
+            te = text_embeds[gi.to(text_embeds.device)] if text_embeds is not None else None
+            ne = null_text_embeds
+            if ne is not None and ne.shape[0] == plan.B and plan.B != 1:
+                ne = ne[gi.to(ne.device)]
         run = model.make_run(plan.my_natoms, te, ne, cond_scale, step_lr, None, seed, plan.mine)
         run.init_state(l_T[gi], x_T[nodes], t_start)
     return run

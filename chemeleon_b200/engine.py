@@ -85,11 +85,46 @@ class DecoderEngine:
 
     # -- FiLM conditioning -------------------------------------------------------
     def text_part(self, text_embeds: torch.Tensor) -> torch.Tensor:
-        """W_cond[:, time_dim:] @ text + b_cond  -> [rows,1024].  Once per prompt, off the hot path."""
+        """W_cond[:, time_dim:] @ text + b_cond  -> [rows,1024] from projected text embeddings [rows,512]
+        (the output of `TextEncoder.get_text_embeds`).  Once per prompt, off the hot path."""
         w = self.w
         if w.film_w_text is None:
             raise ValueError("model has no text conditioning (text_guide=False)")
-        return torch.addmm(w.film_b_cond, text_embeds.to(self.device, torch.float32), w.film_w_text.t()).contiguous()
+        x = text_embeds.to(self.device, torch.float32).contiguous()
+        out = torch.empty(x.shape[0], 2 * self.cfg.hidden_dim, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cb2_linear_f32(x.data_ptr(), x.shape[1], w.film_w_text.data_ptr(), w.film_b_cond.data_ptr(),
+                                               out.data_ptr(), out.shape[1], x.shape[0], out.shape[1], x.shape[1], 0,
+                                               _stream_ptr()), "cb2_linear_f32")
+        return out
+
+    @property
+    def has_text_tail(self) -> bool:
+        return self.w.text_tail is not None and self.w.film_w_text is not None
+
+    def text_condition(self, encoder_embeds: torch.Tensor) -> torch.Tensor:
+        """Language-model embeddings [P, embed_dim] of P distinct prompts -> FiLM text rows [P + 1, 1024]
+        (row P = the unconditional row from the learned null embedding): `TextEncoder.text_emb` +
+        `null_text_embeds` + the text half of `FilmLayer.mlp_cond`, on the device (cb2_text_condition)."""
+        if not self.has_text_tail:
+            raise ValueError("the weights hold no text_encoder.text_emb.* / null_text_embeds (or text_guide=False)")
+        t = self.w.text_tail
+        enc = encoder_embeds.to(self.device, torch.float32).contiguous()
+        if enc.dim() != 2 or enc.shape[1] != t.embed_dim:
+            raise ValueError(f"encoder embeddings must be [n_prompts, {t.embed_dim}]")
+        tt = _lib.TextTail()
+        tt.embed_dim, tt.text_dim = t.embed_dim, t.text_dim
+        for name in ("w1", "b1", "ln_g", "ln_b", "w2", "b2", "null_embeds"):
+            setattr(tt, name, getattr(t, name).data_ptr())
+        tt.w_text, tt.b_cond = self.w.film_w_text.data_ptr(), self.w.film_b_cond.data_ptr()
+        P = enc.shape[0]
+        out = torch.empty(P + 1, 2 * self.cfg.hidden_dim, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            ws = torch.empty(int(self.lib.cb2_text_condition_workspace_bytes(C.byref(tt), P)), dtype=torch.uint8,
+                             device=self.device)
+            _lib.check(self.lib.cb2_text_condition(C.byref(tt), enc.data_ptr() if P else None, P, out.data_ptr(),
+                                                   ws.data_ptr(), ws.numel(), _stream_ptr()), "cb2_text_condition")
+        return out
 
     def film_cond_from_embeddings(self, t_emb: Optional[torch.Tensor], text: Optional[torch.Tensor],
                                   topo: BatchTopology) -> Optional[torch.Tensor]:

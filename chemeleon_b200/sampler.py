@@ -40,17 +40,25 @@ class InjectedNoise:
         self.t_start = int(t_start)
 
 
+class TextCondition:
+    """What a batch is conditioned on: FiLM text rows [R,1024] (device) and, for every (variant, crystal)
+    in the order [cond crystals | null crystals], the row it uses (int32 [2B])."""
+
+    def __init__(self, rows: torch.Tensor, row_of: torch.Tensor):
+        self.rows, self.row_of = rows, row_of
+
+
 class SamplerRun:
     """Device buffers + (optionally captured) step for one batch on one GPU."""
 
-    def __init__(self, engine: DecoderEngine, natoms: Sequence[int], text: Optional[torch.Tensor],
-                 null_text: Optional[torch.Tensor], cond_scale: float, step_lr: float,
+    def __init__(self, engine: DecoderEngine, natoms: Sequence[int], cond: Optional["TextCondition"],
+                 cond_scale: float, step_lr: float,
                  noise: Optional[InjectedNoise] = None, seed: int = 0,
                  graph_gid: Optional[Sequence[int]] = None, use_cuda_graph: bool = True):
         self.eng = engine
         cfg = engine.cfg
         dev = engine.device
-        self.text_guide = text is not None
+        self.text_guide = cond is not None
         V = 2 if self.text_guide else 1
         self.topo: BatchTopology = engine.topology(natoms, V)
         B, N = self.topo.B, self.topo.N
@@ -67,16 +75,14 @@ class SamplerRun:
                                                cfg.sigma_end, cfg.beta_schedule, engine.w.q_mats,
                                                engine.w.q_one_step_mats)
             self.coef = coef.to(dev)
+            # FiLM text rows [<= V*B + 1, 1024] + the row every (variant, crystal) uses: crystals with the
+            # same prompt share a row, all unconditional rows are one row (k_film_cond gathers)
+            self.text_part = torch.zeros(V * B + 1, 2 * cfg.hidden_dim, dtype=torch.float32, device=dev)
+            self.text_row = torch.zeros(V * B, dtype=torch.int32, device=dev)
             if self.text_guide:
-                text = text.to(dev, torch.float32)
-                null_text = null_text.to(dev, torch.float32)
-                if null_text.shape[0] == 1:
-                    null_text = null_text.expand(B, -1)
-                if text.shape[0] != B or null_text.shape[0] != B:
-                    raise ValueError("text embeddings must have one row per crystal")
-                self.text_part = engine.text_part(torch.cat([text, null_text], dim=0))
+                self._set_condition(cond)
             else:
-                self.text_part = engine.w.film_b_cond.unsqueeze(0).expand(B, -1).contiguous()
+                self.text_part[0] = engine.w.film_b_cond
             gid = np.arange(B, dtype=np.int64) if graph_gid is None else np.asarray(graph_gid, dtype=np.int64)
             self.graph_gid = torch.from_numpy(gid).to(dev)
         self.noise = noise
@@ -90,6 +96,7 @@ class SamplerRun:
                                                                   self.flags.data_ptr())
         args = _lib.StepArgs()
         args.coef, args.text_part = self.coef.data_ptr(), self.text_part.data_ptr()
+        args.text_row = self.text_row.data_ptr()
         args.cond_scale = float(cond_scale)
         args.timesteps = cfg.timesteps
         args.precision = engine.precision
@@ -109,15 +116,19 @@ class SamplerRun:
         self.busy = False        # owned by a live generator: must not be handed out again from the run cache
 
     # -- re-use of a captured run with new conditioning (pointers stay valid) -------
-    def reconfigure(self, text: Optional[torch.Tensor], null_text: Optional[torch.Tensor], seed: int,
+    def _set_condition(self, cond: "TextCondition") -> None:
+        rows, row_of = cond.rows, cond.row_of
+        if row_of.numel() != self.V * self.B or rows.shape[0] > self.text_part.shape[0]:
+            raise ValueError("text condition does not match the batch (one row index per variant and crystal)")
+        if int(row_of.max()) >= rows.shape[0] or int(row_of.min()) < 0:
+            raise ValueError("text condition: row index out of range")
+        self.text_part[: rows.shape[0]].copy_(rows, non_blocking=True)
+        self.text_row.copy_(row_of.to(torch.int32), non_blocking=True)
+
+    def reconfigure(self, cond: Optional["TextCondition"], seed: int,
                     graph_gid: Optional[Sequence[int]] = None) -> None:
-        dev = self.eng.device
         if self.text_guide:
-            text = text.to(dev, torch.float32, non_blocking=True)
-            null_text = null_text.to(dev, torch.float32, non_blocking=True)
-            if null_text.shape[0] == 1:
-                null_text = null_text.expand(self.B, -1)
-            self.text_part.copy_(self.eng.text_part(torch.cat([text, null_text], dim=0)))
+            self._set_condition(cond)
         self.seed_dev.fill_(int(seed) & (2 ** 63 - 1))
         if graph_gid is not None:
             self.graph_gid.copy_(torch.as_tensor(np.asarray(graph_gid, dtype=np.int64)), non_blocking=True)
@@ -214,6 +225,9 @@ class ChemeleonB200:
         self.use_cuda_graph = use_cuda_graph
         self.hparams = self.cfg
         self._run_cache = {}
+        self.prompt_embeds = {}          # prompt -> language-model embedding [embed_dim] (host)
+        self.source_hparams = dict(getattr(source, "hparams", {}) or {}) if not isinstance(source, dict) else \
+            dict(source.get("hyper_parameters", {}))
 
     # -- loaders (reference: chemeleon.py:97-135) ----------------------------------
     @classmethod
@@ -222,7 +236,9 @@ class ChemeleonB200:
             raise FileNotFoundError(f"{path_ckpt}: checkpoints are not bundled and cannot be downloaded offline")
         ckpt = torch.load(path_ckpt, map_location="cpu", weights_only=False)
         cfg = SamplerConfig.from_hparams(ckpt.get("hyper_parameters", {}))
-        return cls(ckpt["state_dict"], cfg, text_encoder=text_encoder, **kw)
+        model = cls(ckpt["state_dict"], cfg, text_encoder=text_encoder, **kw)
+        model.source_hparams = dict(ckpt.get("hyper_parameters", {}))
+        return model
 
     @classmethod
     def load_general_text_model(cls, checkpoint_dir: Optional[str] = None, **kw) -> "ChemeleonB200":
@@ -238,9 +254,60 @@ class ChemeleonB200:
         return self
 
     # -- text ------------------------------------------------------------------
+    def set_prompt_embedding(self, prompt: str, embedding: torch.Tensor) -> None:
+        """Register the language-model embedding [embed_dim] of a prompt (what the reference's
+        `TextEncoder.text_encode` returns: BERT class token, CrystalClip projection applied), so that
+        `sample(text_input=prompt, ...)` runs without the language model at hand."""
+        self.prompt_embeds[str(prompt)] = embedding.detach().reshape(-1).to(torch.float32).cpu()
+
+    def condition_from_embeddings(self, B: int, text_embeds: torch.Tensor,
+                                  null_text_embeds: torch.Tensor) -> TextCondition:
+        """Projected text embeddings (outputs of `TextEncoder.get_text_embeds`): cond [B,512], null [1 or B,512]."""
+        dev = self.device
+        text = text_embeds.to(dev, torch.float32, non_blocking=True)
+        null = null_text_embeds.to(dev, torch.float32, non_blocking=True)
+        if text.shape[0] != B or null.shape[0] not in (1, B):
+            raise ValueError("text embeddings must have one row per crystal (null: one row, or one per crystal)")
+        rows = self.engine.text_part(torch.cat([text, null], dim=0))
+        idx = torch.arange(B, dtype=torch.int32, device=dev)
+        null_rows = idx + B if null.shape[0] == B else torch.full((B,), B, dtype=torch.int32, device=dev)
+        return TextCondition(rows, torch.cat([idx, null_rows]))
+
+    def condition_from_encoder(self, encoder_embeds: torch.Tensor, prompt_ids: Sequence[int]) -> TextCondition:
+        """Language-model embeddings [P, embed_dim] of the DISTINCT prompts + the prompt of every crystal:
+        the text tail (text_emb MLP, learned null embedding, FiLM fold) runs on the device, P + 1 rows."""
+        rows = self.engine.text_condition(encoder_embeds)
+        P = rows.shape[0] - 1
+        ids = torch.as_tensor(list(prompt_ids), dtype=torch.int32)
+        if ids.numel() and (int(ids.max()) >= P or int(ids.min()) < 0):
+            raise ValueError("prompt id out of range")
+        row_of = torch.cat([ids, torch.full_like(ids, P)]).to(self.device)
+        return TextCondition(rows, row_of)
+
     def _embed_texts(self, texts: Sequence[str]):
-        if self.text_encoder is None:
-            raise ValueError("string prompts need a text_encoder; pass text_embeds/null_text_embeds instead")
+        """Prompts -> conditioning.  With the checkpoint's own text tail (text_encoder.text_emb.*) only the
+        language-model embedding of each DISTINCT prompt is needed: from `prompt_embeds`
+        (`set_prompt_embedding`) or from `text_encoder.text_encode(prompts, device)`
+        (text_encoder/text_encoder.py:129-184).  Otherwise `text_encoder.get_text_embeds` is called like the
+        reference does (chemeleon.py:364-377)."""
+        texts = [str(t) for t in texts]
+        if self.engine.has_text_tail:
+            distinct = list(dict.fromkeys(texts))
+            missing = [p for p in distinct if p not in self.prompt_embeds]
+            if missing and self.text_encoder is not None and hasattr(self.text_encoder, "text_encode"):
+                enc = self.text_encoder.text_encode(missing, self.device).detach().to(torch.float32).cpu()
+                for p, e in zip(missing, enc):
+                    self.prompt_embeds[p] = e
+                missing = []
+            if not missing:
+                enc = torch.stack([self.prompt_embeds[p] for p in distinct])
+                index = {p: i for i, p in enumerate(distinct)}
+                return self.condition_from_encoder(enc, [index[t] for t in texts]), None
+        if self.text_encoder is None or not hasattr(self.text_encoder, "get_text_embeds"):
+            raise ValueError(
+                "string prompts need either the language-model embedding of every prompt (set_prompt_embedding / a "
+                "text_encoder with text_encode) together with a checkpoint that holds text_encoder.text_emb.*, or a "
+                "text_encoder with get_text_embeds; alternatively pass text_embeds / null_text_embeds")
         te = self.text_encoder.get_text_embeds(list(texts), cond_drop_prob=0.0, device=self.device)
         ne = self.text_encoder.get_text_embeds(list(texts), cond_drop_prob=1.0, device=self.device)
         return te.detach(), ne.detach()
@@ -251,28 +318,30 @@ class ChemeleonB200:
                  graph_gid=None) -> SamplerRun:
         if self.text_guide and text_embeds is None:
             raise ValueError("text_guide model: text embeddings are required")
-        if not self.text_guide:
-            text_embeds = null_text_embeds = None
+        cond = None
+        if self.text_guide:
+            cond = text_embeds if isinstance(text_embeds, TextCondition) else \
+                self.condition_from_embeddings(len(natoms), text_embeds, null_text_embeds)
         if noise is not None:  # parity mode: injected tensors are baked into the step arguments
-            return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, noise, seed,
-                              graph_gid, self.use_cuda_graph)
+            return SamplerRun(self.engine, natoms, cond, cond_scale, step_lr, noise, seed, graph_gid,
+                              self.use_cuda_graph)
         # production mode: a captured run is re-used for every later call with the same batch
         # shape (e.g. composition sweeps); only the conditioning, seed and sample ids change.
         key = (tuple(int(n) for n in natoms), float(cond_scale), float(step_lr))
         run = self._run_cache.get(key)
         if run is not None and run.busy:
             # a live generator (stream=True) owns the cached run: its state must not be shared
-            return SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, None, seed,
-                              graph_gid, self.use_cuda_graph)
+            return SamplerRun(self.engine, natoms, cond, cond_scale, step_lr, None, seed, graph_gid,
+                              self.use_cuda_graph)
         if run is None:
             if len(self._run_cache) >= 4:
                 self._run_cache = {k: r for k, r in self._run_cache.items() if r.busy}
-            run = SamplerRun(self.engine, natoms, text_embeds, null_text_embeds, cond_scale, step_lr, None, seed,
-                             graph_gid, self.use_cuda_graph)
+            run = SamplerRun(self.engine, natoms, cond, cond_scale, step_lr, None, seed, graph_gid,
+                             self.use_cuda_graph)
             self._run_cache[key] = run
         else:
             gid = graph_gid if graph_gid is not None else np.arange(run.B, dtype=np.int64)
-            run.reconfigure(text_embeds, null_text_embeds, seed, gid)
+            run.reconfigure(cond, seed, gid)
         return run
 
     def initial_noise(self, B: int, N: int, seed: int):

@@ -32,7 +32,7 @@ Tensor = torch.Tensor
 
 def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, head_scale: float = 1.0,
                            perturb_ln: bool = True, lattice_identity: bool = False,
-                           lattice_gamma: float = 1.0) -> Dict[str, Tensor]:
+                           lattice_gamma: float = 1.0, text_tail_dim: int = 0) -> Dict[str, Tensor]:
     """Random weights of the reference architecture, keyed like its checkpoint.
 
     Checkpoints are not available offline, so benchmarks and parity tests use
@@ -87,6 +87,13 @@ def random_init_state_dict(cfg: SamplerConfig = SamplerConfig(), seed: int = 0, 
         sd["decoder.final_layer_norm.weight"][0] = 0.0
         sd["decoder.final_layer_norm.bias"][0] = 4.0
         sd["decoder.lattice_out.weight"][:, 0] = lattice_gamma * torch.eye(3).reshape(9) / 4.0
+    if text_tail_dim:
+        # TextEncoder.text_emb / null_text_embeds (text_encoder.py:40-46), torch default inits
+        E = int(text_tail_dim)
+        lin("text_encoder.text_emb.0", E, E)
+        lnorm("text_encoder.text_emb.1", E)
+        lin("text_encoder.text_emb.3", cfg.text_dim, E)
+        sd["text_encoder.null_text_embeds"] = torch.randn(1, E, generator=g)
     sx = schedules.sigma_buffer(cfg.timesteps, cfg.sigma_begin, cfg.sigma_end)
     sd["sigma_scheduler.sigmas"] = sx
     sd["sigma_scheduler.sigmas_norm"] = schedules.sigma_norm_monte_carlo(sx[1:], seed=seed)
@@ -157,6 +164,21 @@ class LayerWeights:
 
 
 @dataclass
+class TextTailWeights:
+    """`TextEncoder.text_emb` + `null_text_embeds` (text_encoder/text_encoder.py:40-46): everything of the
+    text conditioning that comes after the language model."""
+    embed_dim: int
+    text_dim: int
+    w1: Tensor
+    b1: Tensor
+    ln_g: Tensor
+    ln_b: Tensor
+    w2: Tensor
+    b2: Tensor
+    null_embeds: Tensor            # [1, embed_dim]
+
+
+@dataclass
 class PackedWeights:
     cfg: SamplerConfig
     device: torch.device
@@ -180,6 +202,7 @@ class PackedWeights:
     q_mats: Optional[Tensor] = None
     q_one_step_mats: Optional[Tensor] = None
     extra: Dict[str, Tensor] = field(default_factory=dict)
+    text_tail: Optional[TextTailWeights] = None   # present when the state_dict holds text_encoder.text_emb.*
 
 
 def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", tensor_core: bool = True) -> PackedWeights:
@@ -267,6 +290,16 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
         sn = schedules.sigma_norm_monte_carlo(
             schedules.sigma_buffer(cfg.timesteps, cfg.sigma_begin, cfg.sigma_end)[1:])
 
+    tail = None
+    if "text_encoder.text_emb.0.weight" in sd and "text_encoder.null_text_embeds" in sd:
+        tw1 = get("text_encoder.text_emb.0.weight")
+        tw2 = get("text_encoder.text_emb.3.weight")
+        tail = TextTailWeights(
+            embed_dim=int(tw1.shape[1]), text_dim=int(tw2.shape[0]), w1=d(tw1), b1=d(get("text_encoder.text_emb.0.bias")),
+            ln_g=d(get("text_encoder.text_emb.1.weight")), ln_b=d(get("text_encoder.text_emb.1.bias")),
+            w2=d(tw2), b2=d(get("text_encoder.text_emb.3.bias")),
+            null_embeds=d(get("text_encoder.null_text_embeds").reshape(1, -1)))
+
     wp = get("decoder.film_layer.proj.weight")
     return PackedWeights(
         cfg=cfg, device=dev, emb=d(get("decoder.node_embedding.weight")),
@@ -279,4 +312,4 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
         w_head=d(w_head), b_head=d(b_head), w_head_t=head_split_image(w_head),
         w_lat=d(get("decoder.lattice_out.weight")), sigmas_norm=sn,
         q_mats=sd.get("d3pm.q_mats"), q_one_step_mats=sd.get("d3pm.q_one_step_mats"),
-        extra={"film_w_cond": d(w_cond)})
+        extra={"film_w_cond": d(w_cond)}, text_tail=tail)

@@ -168,7 +168,10 @@ typedef struct {
 
 typedef struct {
   const float *coef;           /* [T+1,16] coefficient table (schedules.py) */
-  const float *text_part;      /* [V*B,1024] W_cond[:,128:] @ text + b  (cond rows then null rows) */
+  const float *text_part;      /* [V*B,1024] W_cond[:,128:] @ text + b  (cond rows then null rows); with text_row:
+                                * [n_rows,1024], e.g. the n_prompts + 1 rows cb2_text_condition writes */
+  const int32_t *text_row;     /* optional [V*B]: row of text_part conditioning (variant v, crystal g); crystals that
+                                * share a prompt share a row, every unconditional row is the one null row */
   float cond_scale;
   int32_t timesteps;           /* T: the lattice is clipped to [-6,6] at t == T only (chemeleon.py:424-425) */
   int32_t precision;
@@ -201,6 +204,27 @@ int cb2_embed_nodes(const cb2_model *m, const cb2_batch *b, const int64_t *atom_
  * with the time half tabulated.  t is read from *t_dev. */
 int cb2_film_cond(const cb2_model *m, const cb2_batch *b, const float *text_part,
                   const int32_t *t_dev, float *film_cond /*[V*B,1024]*/, void *stream);
+
+/* ---- text-conditioning tail: TextEncoder.get_text_embeds after the language model
+ * (text_encoder/text_encoder.py:40-45,186-205) folded through the text half of FilmLayer.mlp_cond
+ * (cspnet.py:70-73): once per distinct prompt, off the per-timestep path. ---- */
+typedef struct {
+  int32_t embed_dim;            /* TextEncoder.text_embed_dim (768) */
+  int32_t text_dim;             /* TextEncoder.text_dim (512) */
+  const float *w1, *b1;         /* text_emb.0: Linear(embed_dim, embed_dim) */
+  const float *ln_g, *ln_b;     /* text_emb.1: LayerNorm(embed_dim); text_emb.2 = GELU */
+  const float *w2, *b2;         /* text_emb.3: Linear(embed_dim, text_dim) */
+  const float *null_embeds;     /* [1,embed_dim] TextEncoder.null_text_embeds (cond_drop_prob = 1 replaces every row by it) */
+  const float *w_text;          /* [1024,text_dim] FilmLayer.mlp_cond.0.weight[:, time_dim:] */
+  const float *b_cond;          /* [1024] FilmLayer.mlp_cond.0.bias */
+} cb2_text_tail;
+
+/* text_part[r] = W_text text_emb(r < n_prompts ? enc[r] : null_embeds) + b_cond for r = 0..n_prompts:
+ * rows 0..n_prompts-1 condition on the language-model embeddings enc [n_prompts,embed_dim]
+ * (get_text_embeds(cond_drop_prob=0)), row n_prompts is the unconditional row (cond_drop_prob=1). */
+int cb2_text_condition(const cb2_text_tail *t, const float *enc, int32_t n_prompts,
+                       float *text_part /*[n_prompts+1,1024]*/, void *workspace, size_t workspace_bytes, void *stream);
+size_t cb2_text_condition_workspace_bytes(const cb2_text_tail *t, int32_t n_prompts);
 
 /* C = act(A W^T + bias): the fp32 linear the exact path is built from (tests). */
 int cb2_linear_f32(const float *A, int64_t lda, const float *W, const float *bias, float *C,

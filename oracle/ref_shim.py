@@ -240,3 +240,54 @@ def build_reference_model(seed: int = 0, cfg: dict | None = None):
     model = ref.chemeleon.Chemeleon(cfg)
     model.eval()
     return model
+
+
+# --------------------------------------------------------------------------
+# the REAL reference TextEncoder with a stand-in language model
+# --------------------------------------------------------------------------
+class FakeLanguageModel:
+    """Stands in for the BERT + CrystalClip pair (weights are not downloadable offline): a
+    deterministic "class token" embedding per prompt.  Everything AFTER the language model --
+    `text_emb`, `null_text_embeds`, the keep mask of `get_text_embeds` -- is the reference's own code.
+    Passed to the reference `TextEncoder` as `pretrained_clip_model` (text_encoder.py:48-51)."""
+
+    def __init__(self, table, dim):
+        outer = self
+        self.table, self.dim = table, dim          # prompt -> tensor [dim]
+        self._batch = None
+
+        class _Tokenizer:
+            # tokenizer interface used by TextEncoder.text_encode (text_encoder.py:130-136)
+            def batch_encode_plus(self, batch_text, **kw):
+                outer._batch = list(batch_text)
+                ids = torch.zeros(len(batch_text), 1, dtype=torch.long)
+                return types.SimpleNamespace(input_ids=ids, attention_mask=torch.ones_like(ids))
+
+        class _Encoder(nn.Module):
+            # language-model interface (text_encoder.py:170-175): class token = last_hidden_state[:, 0]
+            def forward(self, input_ids=None, attention_mask=None):
+                emb = torch.stack([outer.table[p] for p in outer._batch]).to(input_ids.device)
+                return types.SimpleNamespace(last_hidden_state=emb[:, None, :])
+
+        self.tokenizer = _Tokenizer()
+        self.text_encoder = _Encoder()
+        self.text_proj = nn.Identity()
+
+
+def load_reference_text_encoder():
+    """The reference's real `TextEncoder` class, imported from its own file (the package-level
+    `chemeleon.text_encoder.text_encoder` entry stays the light stub the sampler tests use)."""
+    load_reference()
+    import importlib.util
+
+    pkg = sys.modules["chemeleon.text_encoder"]
+    init = importlib.util.spec_from_file_location("_cb2_ref_te_init",
+                                                  os.path.join(REFERENCE_ROOT, "chemeleon", "text_encoder", "__init__.py"))
+    m = importlib.util.module_from_spec(init)
+    init.loader.exec_module(m)
+    pkg.MODEL_NAMES, pkg.ARTIFACT_PATHS = m.MODEL_NAMES, m.ARTIFACT_PATHS
+    spec = importlib.util.spec_from_file_location(
+        "_cb2_ref_text_encoder", os.path.join(REFERENCE_ROOT, "chemeleon", "text_encoder", "text_encoder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.TextEncoder

@@ -148,6 +148,35 @@ def run_forward_cases(name="ang_forward"):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def run_text_tail(name="text_tail"):
+    """`TextEncoder.get_text_embeds` of the unmodified reference (text_encoder.py:186-205) with a
+    stand-in language model: per-prompt "class token" embeddings in, projected text embeddings
+    [B, 512] out, for cond_drop_prob = 0 (conditional) and 1 (learned null embedding).  The tail's
+    weights are regenerated by the tests from `weight_seed` (random_init_state_dict(text_tail_dim=768))."""
+    TE = ref_shim.load_reference_text_encoder()
+    cfg = SamplerConfig()
+    seed = 31
+    sd = random_init_state_dict(cfg, seed=seed, text_tail_dim=768)
+    g = torch.Generator().manual_seed(77)
+    prompts = [f"synthetic prompt {i}" for i in range(5)]
+    table = {p: torch.randn(768, generator=g) for p in prompts}
+    te = TE(text_embed_dim=768, text_dim=cfg.text_dim, pretrained_clip_model=ref_shim.FakeLanguageModel(table, 768))
+    res = te.load_state_dict({k[len("text_encoder."):]: v for k, v in sd.items() if k.startswith("text_encoder.")},
+                             strict=False)
+    assert not [k for k in res.missing_keys if k.startswith(("text_emb", "null_text"))], res
+    batch = [prompts[i] for i in (0, 3, 3, 1, 4, 0, 2)]
+    with torch.no_grad():
+        cond = te.get_text_embeds(batch, 0.0, "cpu")
+        null = te.get_text_embeds(batch, 1.0, "cpu")
+    keys = sorted(k for k in sd if k.startswith("text_encoder."))
+    chk = np.array([sum(float(sd[k].double().sum()) for k in keys), sum(float(sd[k].double().abs().sum()) for k in keys)])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, weight_seed=np.int64(seed), weight_checksum=chk,
+                        enc=torch.stack([table[p] for p in prompts]).numpy(), prompt_ids=np.array([0, 3, 3, 1, 4, 0, 2]),
+                        cond=cond.numpy(), null=null.numpy())
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     T = 1000
@@ -182,6 +211,8 @@ if __name__ == "__main__":
              lattice_identity=True, lattice_gamma=0.5)
     if not only or "ang_forward" in only:
         run_forward_cases()
+    if not only or "text_tail" in only:
+        run_text_tail()
     # full-scale heads, first steps only (the dynamics blow up later with random weights)
     run_case("c1_full_6", [6, 6, 6], weight_seed=0, head_scale=1.0, noise_seed=7, text_seed=1,
              n_steps=6, record_ts=[1000, 999, 995], state_ts=[1000, 999, 998, 995, 994])

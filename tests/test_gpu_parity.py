@@ -260,16 +260,20 @@ def test_golden_teacher_forced_steps(O, precision, case):
         a, x, l = model.sample_states(natoms, text, null, float(g["cond_scale"]), float(g["step_lr"]),
                                       noise=noise, t_start=t, t_stop=t - 1, init_state=init)
         flags = model.last_flags.cpu()
+        keep_g = torch.ones(len(natoms), dtype=torch.bool)
         if precision == "tc":
-            oor = _tc_out_of_range(sd, g[f"rec{t}_l_t"])
+            # the step runs the decoder on l_t (predictor) and on l_{t-1} (corrector): either may leave the range
+            oor = _tc_out_of_range(sd, g[f"rec{t}_l_t"]) | _tc_out_of_range(sd, g[f"rec{t}_l_next"])
             assert torch.equal((flags & _lib.FLAG_TC_RANGE) != 0, oor), f"t={t}: range flags {flags} vs {oor}"
-            if bool(oor.any()):
-                continue          # the library said so itself: these states are for exact mode
+            keep_g = ~oor         # flagged crystals: the library said so itself, they are for exact mode
         else:
             assert int(flags.abs().sum()) == 0
-        checked += 1
+        if not bool(keep_g.any()):
+            continue
+        keep_n = keep_g.repeat_interleave(torch.tensor(natoms)).numpy()
+        checked += int(keep_g.sum())
         a_ref = g[f"rec{t}_a_next"]
-        match = float((a.cpu().numpy() == a_ref).mean())
+        match = float((a.cpu().numpy() == a_ref)[keep_n].mean())
         if precision == "fp32":
             assert match == 1.0, f"t={t}: type mismatch"
         else:
@@ -277,10 +281,12 @@ def test_golden_teacher_forced_steps(O, precision, case):
         # the ancestral step multiplies the decoder's lattice error by c0 = 1/sqrt(alpha_t)
         # (= 100 at t = T, chemeleon.py:416-420); the per-step criterion is on the decoder outputs
         c0 = float(1.0 / torch.sqrt(schedules.beta_buffers(1000)["alphas"][t]))
-        assert rel_err(l.cpu(), g[f"rec{t}_l_next"]) < tol * max(1.0, c0), f"t={t} lattice"
-        d = np.abs((x.cpu().numpy() - g[f"rec{t}_x_next"] + 0.5) % 1.0 - 0.5).max()
+        assert rel_err(l.cpu()[keep_g], g[f"rec{t}_l_next"][keep_g.numpy()]) < tol * max(1.0, c0), f"t={t} lattice"
+        d = np.abs((x.cpu().numpy() - g[f"rec{t}_x_next"] + 0.5) % 1.0 - 0.5)[keep_n].max()
         assert d < tol, f"t={t} coords {d}"
-    assert checked >= (2 if case == "c1_tamed_1000" else len(g["record_ts"]))
+    # crystals actually compared: everything, except where untrained heads have blown the lattice up
+    n_all = len(natoms) * len(g["record_ts"])
+    assert checked >= {"c1_tamed_1000": 6, "c1_full_6": 5, "ragged_full_4": 7}.get(case, n_all), checked
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
