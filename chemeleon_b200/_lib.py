@@ -110,6 +110,8 @@ EXPORTS = {
     "cb2_sampler_step": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), C.POINTER(State), C.POINTER(StepArgs),
                                    vp, C.c_size_t, vp]),
     "cb2_launch_count": (C.c_uint64, []),
+    "cb2_frame_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "cb2_pack_frame": (C.c_int, [C.POINTER(Batch), C.POINTER(State), vp, C.c_size_t, vp]),
     "cb2_validity_filter": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_float, C.c_float, vp, vp, vp, vp]),
 }
 

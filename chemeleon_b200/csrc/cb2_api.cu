@@ -43,6 +43,8 @@ int update_predictor(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, c
                      const float *lat_out, cudaStream_t st);
 int update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, const float *head_out,
                      cudaStream_t st);
+size_t frame_bytes(int N, int B);
+int pack_frame(const cb2_batch *b, const cb2_state *s, void *frame, size_t bytes, cudaStream_t st);
 // tensor-core path (cb2_tc.cu)
 int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                       cudaStream_t st);
@@ -369,6 +371,12 @@ int cb2_update_predictor(const cb2_batch *b, cb2_state *s, const cb2_step_args *
 int cb2_update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, const float *head_out,
                          void *stream) {
   return update_corrector(b, s, a, head_out, (cudaStream_t)stream);
+}
+
+size_t cb2_frame_bytes(int32_t n_nodes, int32_t n_graphs) { return frame_bytes(n_nodes, n_graphs); }
+
+int cb2_pack_frame(const cb2_batch *b, const cb2_state *s, void *frame, size_t frame_bytes_, void *stream) {
+  return pack_frame(b, s, frame, frame_bytes_, (cudaStream_t)stream);
 }
 
 int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const cb2_step_args *a,

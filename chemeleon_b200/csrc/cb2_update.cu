@@ -289,4 +289,39 @@ int update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *a, c
   return CB2_OK;
 }
 
+// ---- streaming frames (TrajectoryContainer.get_atoms input, schema.py:57-68, as a compact wire format) ----
+// frame = { int32 t; int32 n_nodes; int32 n_graphs; int32 reserved;
+//           uint8 types[N] (values > 103 -> 0, schema.py:60-62), zero-padded to a multiple of 4;
+//           float coords[N][3]; float lattice[B][9] }
+__global__ void __launch_bounds__(256) k_pack_frame(const int64_t *__restrict__ a, const float *__restrict__ x,
+                                                    const float *__restrict__ l, const int32_t *__restrict__ t_dev,
+                                                    int N, int B, uint8_t *__restrict__ frame) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Np = (N + 3) & ~3;
+  int32_t *hdr = reinterpret_cast<int32_t *>(frame);
+  uint8_t *types = frame + 16;
+  float *coords = reinterpret_cast<float *>(frame + 16 + Np);
+  float *lat = coords + (int64_t)N * 3;
+  if (idx == 0) { hdr[0] = *t_dev; hdr[1] = N; hdr[2] = B; hdr[3] = 0; }
+  if (idx < Np) {
+    long long v = idx < N ? a[idx] : 0;
+    types[idx] = (uint8_t)((v < 0 || v > 103) ? 0 : v);
+  }
+  if (idx < (int64_t)N * 3) coords[idx] = x[idx];
+  if (idx < (int64_t)B * 9) lat[idx] = l[idx];
+}
+
+size_t frame_bytes(int N, int B) { return 16 + (size_t)((N + 3) & ~3) + (size_t)N * 12 + (size_t)B * 36; }
+
+int pack_frame(const cb2_batch *b, const cb2_state *s, void *frame, size_t bytes, cudaStream_t st) {
+  if (!b || !s || !frame || !s->atom_types || !s->frac_coords || !s->lattices || !s->t_dev)
+    return fail(CB2_ERR_BAD_ARG, "pack_frame: null argument");
+  if (bytes < frame_bytes(b->n_nodes, b->n_graphs)) return fail(CB2_ERR_WORKSPACE, "pack_frame: frame buffer too small");
+  const int64_t work = (int64_t)b->n_nodes * 3 > (int64_t)b->n_graphs * 9 ? (int64_t)b->n_nodes * 3 : (int64_t)b->n_graphs * 9;
+  k_pack_frame<<<(unsigned)((work + 4 + 255) / 256), 256, 0, st>>>(s->atom_types, s->frac_coords, s->lattices, s->t_dev,
+                                                                  b->n_nodes, b->n_graphs, (uint8_t *)frame);
+  CB2_LAUNCH_OK("k_pack_frame");
+  return CB2_OK;
+}
+
 }  // namespace cb2

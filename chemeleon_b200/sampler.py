@@ -399,8 +399,14 @@ class ChemeleonB200:
     # -- reference API ---------------------------------------------------------------
     def _sample_generator(self, natoms: Union[int, List[int]], texts: Optional[Union[str, List[str]]] = None,
                           cond_scale: float = 2.0, step_lr: float = 1e-5, *, text_embeds=None,
-                          null_text_embeds=None, noise=None, seed: int = 0) -> Iterator[List]:
-        """Yields `List[Atoms]` once per timestep (T items), like the reference generator."""
+                          null_text_embeds=None, noise=None, seed: int = 0, frames: bool = False,
+                          depth: int = 4) -> Iterator[List]:
+        """Yields once per timestep (T items), like the reference generator: `List[Atoms]`, or with
+        `frames=True` the compact wire-format `streaming.Frame` of the step.  The GPU is not stalled:
+        the sampling stream runs up to `depth` timesteps ahead of the frame being handed out (packed
+        on the device, copied into a pinned ring buffer on a side stream)."""
+        from .streaming import FrameStreamer
+
         if isinstance(natoms, int):
             natoms = [natoms]
         if isinstance(texts, str):
@@ -418,9 +424,17 @@ class ChemeleonB200:
                     run.init_state(noise.l_T, noise.x_T)
                 else:
                     run.init_state(*self.initial_noise(run.B, run.N, seed))
-                for _t in range(self.cfg.timesteps, 0, -1):
-                    run.step()
-                    yield self._to_atoms(run.a, run.x, run.l, natoms)
+                streamer = FrameStreamer(run, depth)
+                T = self.cfg.timesteps
+                done = 0
+                for _ in range(T):
+                    while done < T and streamer.pending < streamer.depth:
+                        with torch.cuda.device(self.device):
+                            run.step()
+                            streamer.push()
+                        done += 1
+                    frame = streamer.pop()
+                    yield frame if frames else frame.to_atoms(natoms)
                 self.last_flags = run.flags.clone()
             finally:
                 run.busy = False

@@ -270,6 +270,16 @@ int cb2_update_corrector(const cb2_batch *b, cb2_state *s, const cb2_step_args *
 int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const cb2_step_args *a,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Streaming / trajectory wire format (replaces the per-step device->host copy + ase.Atoms construction of
+ * TrajectoryContainer.get_atoms, schema.py:57-83, and the JSON of Atoms the reference server streams,
+ * app/server.py:49-52): one compact frame per timestep, packed on the device so that a single async
+ * copy into a pinned ring buffer moves it.  Layout (little endian):
+ *   int32 t (timestep index the state belongs to), int32 n_nodes, int32 n_graphs, int32 0;
+ *   uint8 types[n_nodes] (values > 103 -> 0 like schema.py:60-62), zero-padded to a multiple of 4 bytes;
+ *   float frac_coords[n_nodes][3]; float lattice[n_graphs][9]. */
+size_t cb2_frame_bytes(int32_t n_nodes, int32_t n_graphs);
+int cb2_pack_frame(const cb2_batch *b, const cb2_state *s, void *frame /*device*/, size_t frame_bytes, void *stream);
+
 /* Validity pre-filter of finished structures on the device: restates
  * chemeleon/scripts/evaluate.py:177-189 (max(lattice.abc) > max_length; smallest positive
  * periodic distance < min_distance) and sample_target_composition.py:57-62 (reduced

@@ -208,3 +208,25 @@ def test_weight_packing_layouts():
     wc = sd["decoder.film_layer.mlp_cond.0.weight"]
     assert torch.allclose(pw.film_time_table[321], wc[:, :128] @ te[321], atol=1e-5)
     assert pw.w_head.shape == (128, 512) and torch.equal(pw.w_head[104:107], sd["decoder.coord_out.weight"])
+
+
+def test_frame_wire_format_roundtrip():
+    """streaming.Frame parses the layout documented in include/chemeleon_b200.h (cb2_pack_frame)."""
+    from chemeleon_b200.streaming import Frame
+
+    N, B = 7, 2
+    npad = (N + 3) & ~3
+    buf = np.zeros(16 + npad + 12 * N + 36 * B, dtype=np.uint8)
+    buf[:16].view(np.int32)[:] = [41, N, B, 0]
+    buf[16:16 + N] = [8, 22, 8, 3, 25, 8, 0]
+    x = np.arange(3 * N, dtype=np.float32) / 32.0
+    l = np.arange(9 * B, dtype=np.float32) + 1
+    buf[16 + npad:16 + npad + 12 * N] = x.view(np.uint8)
+    buf[16 + npad + 12 * N:] = l.view(np.uint8)
+    f = Frame.from_bytes(buf.tobytes())
+    assert (f.t, f.n_nodes, f.n_graphs) == (41, N, B)
+    assert f.types.tolist() == [8, 22, 8, 3, 25, 8, 0]
+    assert np.array_equal(f.frac_coords.reshape(-1), x) and np.array_equal(f.lattices.reshape(-1), l)
+    atoms = f.to_atoms([4, 3])
+    assert [len(a) for a in atoms] == [4, 3]
+    assert sorted(atoms[0].get_atomic_numbers().tolist()) == [3, 8, 8, 22]

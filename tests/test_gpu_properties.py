@@ -178,3 +178,34 @@ def test_driver_samples_all_buckets_as_one_batch():
     a2, x2, l2 = model.sample_states(natoms, cond, None, seed=9)
     assert torch.equal(a2, a)
     assert torch.allclose(x2, x, atol=1e-5) and torch.allclose(l2.reshape(-1, 9), l.reshape(-1, 9), atol=1e-5, rtol=1e-5)
+
+
+def test_streaming_frames_match_the_atoms_generator():
+    """stream=True: frames packed on the device and copied on a side stream (wire format of
+    include/chemeleon_b200.h) carry exactly what the List[Atoms] generator yields, one per timestep."""
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.sampler import ChemeleonB200
+    from chemeleon_b200.streaming import Frame
+    from chemeleon_b200.weights import random_init_state_dict
+
+    cfg = SamplerConfig(timesteps=9)
+    model = ChemeleonB200(random_init_state_dict(cfg, seed=0, head_scale=0.01, lattice_identity=True), cfg)
+    g = torch.Generator().manual_seed(0)
+    natoms = [5, 3, 7]
+    emb = dict(text_embeds=torch.randn(3, cfg.text_dim, generator=g), null_text_embeds=torch.randn(1, cfg.text_dim, generator=g))
+    frames = list(model._sample_generator(natoms, None, 2.0, 1e-5, **emb, seed=4, frames=True, depth=3))
+    atoms = list(model._sample_generator(natoms, None, 2.0, 1e-5, **emb, seed=4, depth=2))
+    assert len(frames) == cfg.timesteps == len(atoms)
+    assert [f.t for f in frames] == list(range(cfg.timesteps - 1, -1, -1))      # index of the state, like trajectory[t-1]
+    for f, ats in zip(frames, atoms):
+        assert f.n_nodes == 15 and f.n_graphs == 3 and len(f.to_bytes()) == 16 + 16 + 15 * 12 + 3 * 36
+        back = Frame.from_bytes(f.to_bytes()).to_atoms(natoms)
+        for a, b in zip(back, ats):
+            assert (a.get_atomic_numbers() == b.get_atomic_numbers()).all()
+            assert abs(a.get_scaled_positions() - b.get_scaled_positions()).max() == 0.0
+            assert abs(a.get_cell() - b.get_cell()).max() == 0.0
+    # the last frame is the final state of the plain call
+    final = model.sample_batch(natoms, **emb, seed=4)
+    for a, b in zip(frames[-1].to_atoms(natoms), final):
+        assert (a.get_atomic_numbers() == b.get_atomic_numbers()).all()
+        assert abs(a.get_scaled_positions() - b.get_scaled_positions()).max() < 1e-6
