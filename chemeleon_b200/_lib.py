@@ -20,6 +20,7 @@ TILE_ROWS = 128
 PRECISION_FP32 = 0
 PRECISION_TC_F16 = 1
 MODEL_EDGE_SINGLE_CTA = 1
+PACK_KMAJOR, PACK_FD, PACK_ROW_BLOCKS, PACK_HEAD_SPLIT = 0, 1, 2, 3
 FLAG_NONFINITE = 1
 FLAG_TC_RANGE = 2
 TC_RANGE_LIMIT = 96.0
@@ -110,6 +111,8 @@ EXPORTS = {
     "cb2_sampler_step": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), C.POINTER(State), C.POINTER(StepArgs),
                                    vp, C.c_size_t, vp]),
     "cb2_launch_count": (C.c_uint64, []),
+    "cb2_pack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "cb2_pack_weights": (C.c_int, [C.c_int32, vp, C.c_int32, C.c_int32, vp, C.c_size_t]),
     "cb2_frame_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "cb2_pack_frame": (C.c_int, [C.POINTER(Batch), C.POINTER(State), vp, C.c_size_t, vp]),
     "cb2_validity_filter": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_float, C.c_float, vp, vp, vp, vp]),

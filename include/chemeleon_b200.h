@@ -193,6 +193,23 @@ int cb2_abi_version(void);
 const char *cb2_last_error(void);
 int cb2_check_device(int device);            /* CB2_OK iff compute capability 10.x */
 
+/* ---- operand images for the tensor-core path, packed on the HOST (pure CPU code) ----
+ * What weights.pack_weights does in Python, for hosts without it: fp32 row-major [rows,K] (a torch
+ * Linear weight) -> the fp16 image the kernels stream.  kind:
+ *   CB2_PACK_KMAJOR      [K/8][rows][8]  ("K-major, no swizzle": core matrix = 8 rows x 16 B)   w_hij_t, wn1_t, wn2_t, film_wp_t
+ *   CB2_PACK_FD          the same with the K columns of W_fd permuted from the reference order (sin block | cos block,
+ *                        cspnet.py:49-51) to d*2F + 2k + {sin,cos}                              w_fd_t
+ *   CB2_PACK_ROW_BLOCKS  one K-major image per block of 128 rows: [rows/128][K/8][128][8]        w2_t
+ *   CB2_PACK_HEAD_SPLIT  16-byte header {float 1/s} + image [3K/8][256][8] of s [w_hi | w_hi | w_lo]
+ *                        (split precision, power-of-two scale s, rows padded to 256)             w_head_t */
+#define CB2_PACK_KMAJOR 0
+#define CB2_PACK_FD 1
+#define CB2_PACK_ROW_BLOCKS 2
+#define CB2_PACK_HEAD_SPLIT 3
+size_t cb2_pack_bytes(int32_t kind, int32_t rows, int32_t K);
+int cb2_pack_weights(int32_t kind, const float *w /*host [rows,K]*/, int32_t rows, int32_t K, void *out /*host*/,
+                     size_t out_bytes);
+
 /* Workspace one forward / step of model `m` needs for this batch (bytes). */
 size_t cb2_workspace_bytes(const cb2_model *m, const cb2_batch *batch, int precision);
 

@@ -230,3 +230,44 @@ def test_frame_wire_format_roundtrip():
     atoms = f.to_atoms([4, 3])
     assert [len(a) for a in atoms] == [4, 3]
     assert sorted(atoms[0].get_atomic_numbers().tolist()) == [3, 8, 8, 22]
+
+
+def test_pack_weights_c_matches_python_packer(lib):
+    """cb2_pack_weights (host C code, for non-Python hosts) produces bit-for-bit the operand images
+    weights.pack_weights builds: K-major tiles, W_fd column permutation, W2 row blocks, split-precision head."""
+    from chemeleon_b200 import _lib
+    from chemeleon_b200.weights import fd_column_order, tile_k_major
+
+    g = torch.Generator().manual_seed(0)
+
+    def c_pack(kind, w):
+        rows, K = w.shape
+        nb = int(lib.cb2_pack_bytes(kind, rows, K))
+        out = torch.zeros(nb // 2, dtype=torch.float16)
+        w = w.contiguous()
+        _lib.check(lib.cb2_pack_weights(kind, w.data_ptr(), rows, K, out.data_ptr(), nb), "cb2_pack_weights")
+        return out
+
+    w = torch.randn(512, 1024, generator=g) * 0.05
+    assert torch.equal(c_pack(_lib.PACK_KMAJOR, w).view(torch.int16), tile_k_major(w).reshape(-1).view(torch.int16))
+    wfd = torch.randn(512, 768, generator=g) * 0.03
+    assert torch.equal(c_pack(_lib.PACK_FD, wfd).view(torch.int16),
+                       tile_k_major(wfd[:, fd_column_order(128)]).reshape(-1).view(torch.int16))
+    w2 = torch.randn(512, 512, generator=g) * 0.04
+    blocks = torch.cat([tile_k_major(w2[i:i + 128]) for i in range(0, 512, 128)], dim=0)
+    assert torch.equal(c_pack(_lib.PACK_ROW_BLOCKS, w2).view(torch.int16), blocks.reshape(-1).view(torch.int16))
+    # head: same construction as weights.head_split_image
+    import math
+    wh = torch.zeros(128, 512)
+    wh[:107] = torch.randn(107, 512, generator=g) * 0.04
+    s = 2.0 ** math.floor(math.log2(1024.0 / float(wh.abs().max())))
+    ws = wh.double() * s
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.double()).to(torch.float16)
+    full = torch.zeros(256, 1536, dtype=torch.float16)
+    full[:128] = torch.cat([hi, hi, lo], dim=1)
+    blob = torch.zeros(8 + full.numel(), dtype=torch.float16)
+    blob[:2].view(torch.float32)[0] = 1.0 / s
+    blob[8:] = tile_k_major(full).reshape(-1)
+    assert torch.equal(c_pack(_lib.PACK_HEAD_SPLIT, wh).view(torch.int16), blob.view(torch.int16))
+    assert lib.cb2_pack_weights(_lib.PACK_KMAJOR, w.data_ptr(), 512, 1024, blob.data_ptr(), 16) == -5
