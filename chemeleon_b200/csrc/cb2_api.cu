@@ -184,12 +184,14 @@ static int decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_for
   const int N = b->n_nodes, B = b->n_graphs, V = b->n_variants;
   const int64_t VN = (int64_t)V * N;
   if (N == 0) return CB2_OK;
+  NvtxRange r_fwd(io->coords_only ? "cb2:forward(corrector)" : "cb2:forward(predictor)");
   CB2_TRY(launch_embed(io->atom_types, m->emb, w.h, N, V, st));
   if (io->precision == CB2_PRECISION_FP32) {
     CB2_TRY(f32_forward_layers(m, b, io, w, st));
   } else {
     CB2_TRY(tc_forward_layers(m, b, io, w, st));
   }
+  NvtxRange r_heads("cb2:heads");
   float *hf = io->node_features ? io->node_features : w.hf;
   const bool tc_heads = io->precision != CB2_PRECISION_FP32 && m->w_head_t != nullptr;
   CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, VN, st));
@@ -406,10 +408,15 @@ int cb2_sampler_step(const cb2_model *m, const cb2_batch *b, cb2_state *s, const
   io.coords_only = 0;
   io.precision = a->precision;
   io.flags = s->flags;
+  NvtxRange r_step("cb2:sampler_step");
   CB2_TRY(decoder_forward(m, b, &io, fw, st));                        // predictor (cond | null)
-  CB2_TRY(update_predictor(b, s, a, sw.head_out, sw.lat_out, st));
+  {
+    NvtxRange r("cb2:update(predictor)");
+    CB2_TRY(update_predictor(b, s, a, sw.head_out, sw.lat_out, st));
+  }
   io.coords_only = 1;
   CB2_TRY(decoder_forward(m, b, &io, fw, st));                        // corrector
+  NvtxRange r("cb2:update(corrector)");
   CB2_TRY(update_corrector(b, s, a, sw.head_out, st));
   return CB2_OK;
 }

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/chemeleon_b200.h"
 
 namespace cb2 {
@@ -43,6 +45,15 @@ void count_launch(int n = 1);
     int _s = (expr);                \
     if (_s != CB2_OK) return _s;    \
   } while (0)
+
+// ---- tracing: NVTX ranges around the phases of a forward / timestep; header-only
+// NVTX v3 costs a null-pointer check per call when no profiler is attached ----
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // ---- workspace carving ------------------------------------------------------
 struct Arena {

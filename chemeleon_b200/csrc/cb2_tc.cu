@@ -364,22 +364,29 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
     const cb2_layer_weights &L = m->layers[li];
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
+    NvtxRange r_layer("cb2:csp_layer");
     if (io->film_cond != nullptr) {
       // FiLM projection + LN + FiLM + SiLU + residual + layer LN in one kernel (y stays in TMEM)
+      NvtxRange r("cb2:film");
       CB2_TRY(launch_tc_film(m, L, b, io->film_cond, w.h16, w.h, w.cat16, sms, st));
     } else {
       CB2_TRY(launch_film_apply(nullptr, w.h, nullptr, b->node2graph, m->film_g, m->film_b, L.ln_g, L.ln_b,
                                 nullptr, 0, w.cat16, 0, H2, N, B, V, st));
     }
     {
+      NvtxRange r("cb2:hoist");
       TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T in fp16; the per-crystal lattice term stays in fp32 (cg)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
       a.C16r = reinterpret_cast<__half *>(w.P); a.ldc16r = H2;
       CB2_TRY(launch_tc_linear(a, st));
     }
-    CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P),
-                          w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
     {
+      NvtxRange r("cb2:edge");
+      CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P),
+                            w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
+    }
+    {
+      NvtxRange r("cb2:node_mlp");
       TcLinearArgs a{};   // z = SiLU([hn|agg] Wn1^T + bn1)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H2; a.Wt = (const __half *)L.wn1_t; a.Nw = H;
       a.C16 = w.z16; a.c16_kt = H; a.bias = L.bn1; a.silu = 1;

@@ -42,7 +42,7 @@ __device__ int g_edge2_it;
 #define E1_STAMP(k)                                                                         \
   do {                                                                                      \
     if (blockIdx.x == 0 && threadIdx.x == 0 && g_edge2_it >= 1 && g_edge2_it <= 3)          \
-      g_edge2_dbg[(g_edge2_it - 1) * 96 + 32 + (k)] = clock64();                            \
+      g_edge2_dbg[(g_edge2_it - 1) * 96 + 40 + (k)] = clock64();                            \
   } while (0)
 #endif
 #include "cb2_tc_edge_epi.cuh"
@@ -283,10 +283,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 
     // a1^v lives in CTA v: own shared memory, or the peer's through st.async (completing on the peer's a1_rx)
     const uint32_t a1_off = sbase + (uint32_t)((c1 / 8) * 2048 + (c1 % 8) * 16);
-    const A1Dst a1_local{a1_off, 0u}, a1_remote{mapa_shared(a1_off, rank ^ 1u), mapa_shared(a1_rx, rank ^ 1u)};
-    const A1Dst a1_dst = e_v == (int)rank ? a1_local : a1_remote;          // variant-per-thread E1
-    const A1Dst a1_to0 = rank == 0 ? a1_local : a1_remote;                 // both-variants E1: a1^0 -> CTA 0, a1^1 -> CTA 1
-    const A1Dst a1_to1 = rank == 1 ? a1_local : a1_remote;
+    const A1Dst a1_dst = e_v == (int)rank ? A1Dst{a1_off, 0u}
+                                          : A1Dst{mapa_shared(a1_off, rank ^ 1u), mapa_shared(a1_rx, rank ^ 1u)};
     const float bias_o1 = __ldg(g.b2 + 256 * rank + 128 + q * 32 + lane);     // O1 re-uses the X columns
     // E2
     const uint32_t taddr_o = tq + (e_u == 0 ? 256 : 0) + 128 * e_v;
@@ -412,22 +410,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       if (lane == 0 && q == 0) T2_STAMP(9 + 8 * grp);
       const uint32_t *t_oi = tab + buf * 256;
       const E1Cg cgk{g.cg ? g.cg + c1 : nullptr, g.node2graph, 0u, n >= 4 ? tab_g + buf * 32 : nullptr};
-      // ---- E1: a1^v = SiLU(X + P^v_i + cg + P^v_j), a1^v into CTA v ----
-      if (n >= 4 && n <= CB2_E1_PAIR_MAXN) {
-        // thread = (channel of unit e_u, column half e_v): X is read once, both variants leave from here
-        const uint32_t tx = taddr_x + 64 * e_v;
-        if (e_v == 0) e1_pair_dispatch<0>(n, tx, g.P + c1, (size_t)g.N * H2, cgk, t_oi, t_oi + 128, a1_to0, a1_to1, x_full, it & 1);
-        else e1_pair_dispatch<1>(n, tx, g.P + c1, (size_t)g.N * H2, cgk, t_oi, t_oi + 128, a1_to0, a1_to1, x_full, it & 1);
-        if (lane == 0 && q == 0) T2_STAMP(10 + 8 * grp);
-        tc_fence_before_sync();                      // the columns this thread has just read are its own to re-load
-      } else {
-        // thread = (channel of unit e_u, variant e_v), all 128 columns; X_u is read by two warps per lane quarter
-        e1_dispatch(n, taddr_x, Pc, cgk, t_oi, t_oi + 128, a1_dst, x_full, it & 1);
-        if (lane == 0 && q == 0) T2_STAMP(10 + 8 * grp);
-        tc_fence_before_sync();
-        asm volatile("bar.sync %0, 256;" ::"r"(2 + e_u) : "memory");
-        tc_fence_after_sync();
-      }
+      // ---- E1: a1^v = SiLU(X + P^v_i + cg + P^v_j) for (unit e_u, variant e_v), into CTA e_v ----
+      // thread = (channel of unit e_u, variant e_v), all 128 columns; X_u is read by two warps per lane quarter.
+      // (A both-variants-per-thread form that reads X once -- half the TMEM reads -- was measured 12 % SLOWER:
+      // 3.61 vs 3.23 ms per launch at C3; every thread then feeds a local and a remote store stream.)
+      e1_dispatch(n, taddr_x, Pc, cgk, t_oi, t_oi + 128, a1_dst, x_full, it & 1);
+      if (lane == 0 && q == 0) T2_STAMP(10 + 8 * grp);
+      tc_fence_before_sync();
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + e_u) : "memory");
+      tc_fence_after_sync();
       // the X columns become O1 columns, pre-loaded with b2
       fill_cols(tq + e_u * 128 + e_v * 64, 64, __float_as_uint(bias_o1));
       fence_proxy_async_smem();                      // own a1 stores -> async proxy (st.async needs no producer fence)
@@ -447,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       mbar_wait(o_full(e_u), it & 1);
       tc_fence_after_sync();
       if (lane == 0 && q == 0) T2_STAMP(13 + 8 * grp);
-      e2_dispatch<true>(n, taddr_o, bias_o, t_oi, out, agg_ld);
+      e2_dispatch(n, taddr_o, bias_o, t_oi, out, agg_ld);
       tc_fence_before_sync();
       if (lane == 0 && q == 0) T2_STAMP(14 + 8 * grp);
       if (has_next) refill();

@@ -37,19 +37,7 @@ __device__ __forceinline__ void e2_store(const uint32_t *t_oi, int seg0, __half 
   }
 }
 
-// two SiLUs with one MUFU op, fp32 in / fp32 out: h = x/2, tanh.approx.f16x2 on the pair rounded to
-// fp16, x sigmoid(x) = h + h tanh(h) in fp32 (E2 of the pair kernel is MUFU-bound: 2 x 65536 SiLUs per tile)
-__device__ __forceinline__ void silu2_f32(float a, float b, float &ya, float &yb) {
-  const float ha = 0.5f * a, hb = 0.5f * b;
-  const uint32_t hh = pack_half2_sat(ha, hb);
-  uint32_t t;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hh));
-  const __half2 t2 = *reinterpret_cast<const __half2 *>(&t);
-  ya = fmaf(ha, __low2float(t2), ha);
-  yb = fmaf(hb, __high2float(t2), hb);
-}
-
-template <int N, bool PAIRED = false>
+template <int N>
 __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
                                      AggStride ld_agg) {
   const int n = N > 0 ? N : n_rt;
@@ -66,16 +54,10 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
     if (cb < 3) tmem_ld32(taddr + (cb + 1) * 32, nxt);   // next chunk's TMEM read overlaps this chunk's math
     float t[32];
 #pragma unroll
-    // fp32 tanh here (one MUFU op per element): measured as fast as the paired fp16 form -- E2 of a
-    // unit runs on four warps and is latency-bound -- and the mean is taken over unrounded values
-    for (int j = 0; j < 32; j += 2) {                                         // b2 is already in the accumulator
-      if constexpr (PAIRED) {
-        silu2_f32(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), t[j], t[j + 1]);
-      } else {
-        t[j] = silu_fast(__uint_as_float(acc[j]));
-        t[j + 1] = silu_fast(__uint_as_float(acc[j + 1]));
-      }
-    }
+    // fp32 tanh here (one MUFU op per element): the paired fp16 form (tanh.approx.f16x2, one MUFU op per two
+    // SiLUs) was measured slower in both edge kernels (more issue slots: E2 is latency / issue bound) at 1.5x
+    // the error, and the mean is better taken over unrounded values
+    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       sum += t[j];
@@ -94,11 +76,10 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
   }
 }
 
-template <bool PAIRED = false>
 __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, const uint32_t *t_oi, __half *out,
                                             AggStride ld_agg) {
   switch (n) {
-#define CB2_E2_CASE(N) case N: e2_unit<N, PAIRED>(n, taddr, bias, t_oi, out, ld_agg); break;
+#define CB2_E2_CASE(N) case N: e2_unit<N>(n, taddr, bias, t_oi, out, ld_agg); break;
     CB2_E2_CASE(1) CB2_E2_CASE(2) CB2_E2_CASE(3) CB2_E2_CASE(4) CB2_E2_CASE(5) CB2_E2_CASE(6) CB2_E2_CASE(7)
     CB2_E2_CASE(8) CB2_E2_CASE(9) CB2_E2_CASE(10) CB2_E2_CASE(11) CB2_E2_CASE(12) CB2_E2_CASE(13) CB2_E2_CASE(14)
     CB2_E2_CASE(15) CB2_E2_CASE(16) CB2_E2_CASE(17) CB2_E2_CASE(18) CB2_E2_CASE(19) CB2_E2_CASE(20) CB2_E2_CASE(21)
@@ -106,7 +87,7 @@ __device__ __forceinline__ void e2_dispatch(int n, uint32_t taddr, float bias, c
     CB2_E2_CASE(29) CB2_E2_CASE(30) CB2_E2_CASE(31) CB2_E2_CASE(32) CB2_E2_CASE(33) CB2_E2_CASE(34) CB2_E2_CASE(35)
     CB2_E2_CASE(36) CB2_E2_CASE(37) CB2_E2_CASE(38) CB2_E2_CASE(39) CB2_E2_CASE(40)
 #undef CB2_E2_CASE
-    default: e2_unit<0, PAIRED>(n, taddr, bias, t_oi, out, ld_agg); break;
+    default: e2_unit<0>(n, taddr, bias, t_oi, out, ld_agg); break;
   }
 }
 
@@ -242,7 +223,7 @@ __device__ __noinline__ void e1_unit(uint32_t taddr, const __half *Pc, E1Cg cgk,
         e1_store(a1_dst, (hb * 2 + p) * 128, w[0], w[1], w[2], w[3]);
       }
       if (hb == 0) E1_STAMP(2);
-      if (hb == 3) E1_STAMP(3);
+      if (hb == 7) E1_STAMP(3);
     }
   }
 }
@@ -261,116 +242,6 @@ __device__ __forceinline__ void e1_dispatch(int n, uint32_t taddr, const __half 
     CB2_E1_CASE(38) CB2_E1_CASE(39) CB2_E1_CASE(40)
 #undef CB2_E1_CASE
     default: e1_unit<0>(taddr, Pc, cgk, t_oi, t_oj, a1_dst, acc1_full, parity); break;
-  }
-}
-
-// ---- E1 of the CTA-pair kernel, both CFG variants per thread ----
-// thread = (channel, half of the tile's 128 edge columns): X is read from TMEM ONCE and turned into
-// a1 of both variants (the variant-per-thread form reads it twice; E1 is TMEM-read / issue bound and sits
-// between GEMM1 and GEMM2 with the tensor pipe idle).  P_j of the two variants is kept packed (fp16 pair
-// per register), the segment terms P_i + cg in fp32.  N <= CB2_E1_PAIR_MAXN (register budget).
-#define CB2_E1_PAIR_MAXN 24
-template <int N, int HALF>
-__device__ __noinline__ void e1_pair_unit(uint32_t taddr, const __half *Pc0, size_t vstride, E1Cg cgk, const uint32_t *t_oi,
-                                          const uint32_t *t_oj, A1Dst dst0, A1Dst dst1, uint32_t x_full, uint32_t parity) {
-  constexpr int S = 128 / N;
-  constexpr int E0 = 64 * HALF;
-  constexpr int S_LO = E0 / N;                                   // first segment touching this half
-  constexpr int S_HI = (E0 + 63) / N < S ? (E0 + 63) / N : S - 1; // last one (rows >= S*N are padding)
-  constexpr int SH = S_HI >= S_LO ? S_HI - S_LO + 1 : 0;
-  const __half *Pc1 = Pc0 + vstride;
-  uint32_t oiv[SH > 0 ? SH : 1];
-  __half pi0[SH > 0 ? SH : 1], pi1[SH > 0 ? SH : 1], pj0[N], pj1[N];
-  float cgv[SH > 0 ? SH : 1];
-  uint32_t cur = 0;
-  if constexpr (SH > 0) {
-#pragma unroll
-    for (int s = 0; s < SH; s++) oiv[s] = t_oi[(S_LO + s) * N];
-    cur = t_oj[S_LO * N];                                        // P_j offset of the first row of that crystal's segment
-#pragma unroll
-    for (int s = 0; s < SH; s++) {
-      const uint32_t oi = oiv[s] == TE_PAD ? 0u : oiv[s];
-      pi0[s] = Pc0[oi];
-      pi1[s] = Pc1[oi];
-      cgv[s] = 0.f;
-      if (cgk.cgc != nullptr && oiv[s] != TE_PAD) {
-        const uint32_t gidx = cgk.seg_g ? cgk.seg_g[S_LO + s] : (uint32_t)__ldg(cgk.n2g + ((oi >> 10) - cgk.vbase));
-        cgv[s] = __ldg(cgk.cgc + (size_t)gidx * H);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-      pj0[k] = Pc0[cur + (uint32_t)k * (uint32_t)H2];
-      pj1[k] = Pc1[cur + (uint32_t)k * (uint32_t)H2];
-    }
-  }
-  MBAR_WAIT_WORKER(x_full, parity);
-  tc_fence_after_sync();
-  float piv0[SH > 0 ? SH : 1], piv1[SH > 0 ? SH : 1];
-  uint32_t pj01[N];
-  if constexpr (SH > 0) {
-#pragma unroll
-    for (int s = 0; s < SH; s++) {
-      piv0[s] = oiv[s] == TE_PAD ? 0.f : __half2float(pi0[s]) + cgv[s];
-      piv1[s] = oiv[s] == TE_PAD ? 0.f : __half2float(pi1[s]) + cgv[s];
-    }
-#pragma unroll
-    for (int k = 0; k < N; k++) pj01[k] = (uint32_t)__half_as_ushort(pj0[k]) | ((uint32_t)__half_as_ushort(pj1[k]) << 16);
-  }
-  uint32_t accA[16], accB[16];
-  tmem_ld16(taddr, accA);
-#pragma unroll
-  for (int hb = 0; hb < 4; hb++) {
-    tmem_ld_wait();
-    uint32_t (&acc)[16] = (hb & 1) ? accB : accA;
-    uint32_t (&nxt)[16] = (hb & 1) ? accA : accB;
-    if (hb < 3) tmem_ld16(taddr + (hb + 1) * 16, nxt);
-    float x0[16], x1[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int e = E0 + hb * 16 + j;
-      x0[j] = x1[j] = __uint_as_float(acc[j]);
-      if (e < S * N) {
-        if (e % N == 0 && e > E0) {              // segment start inside this half: same crystal as before?
-          const uint32_t oj0 = t_oj[e];
-          if (oj0 != cur) {
-            cur = oj0;
-#pragma unroll
-            for (int k = 0; k < N; k++)
-              pj01[k] = (uint32_t)__half_as_ushort(Pc0[cur + (uint32_t)k * (uint32_t)H2]) |
-                        ((uint32_t)__half_as_ushort(Pc1[cur + (uint32_t)k * (uint32_t)H2]) << 16);
-          }
-        }
-        const __half2 pj = *reinterpret_cast<const __half2 *>(&pj01[e % N]);
-        x0[j] += piv0[e / N - S_LO] + __low2float(pj);
-        x1[j] += piv1[e / N - S_LO] + __high2float(pj);
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-      uint32_t w0[4], w1[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        w0[e] = silu2_half(x0[8 * p + 2 * e], x0[8 * p + 2 * e + 1]);
-        w1[e] = silu2_half(x1[8 * p + 2 * e], x1[8 * p + 2 * e + 1]);
-      }
-      e1_store(dst0, (HALF * 8 + hb * 2 + p) * 128, w0[0], w0[1], w0[2], w0[3]);
-      e1_store(dst1, (HALF * 8 + hb * 2 + p) * 128, w1[0], w1[1], w1[2], w1[3]);
-    }
-  }
-}
-
-template <int HALF>
-__device__ __forceinline__ void e1_pair_dispatch(int n, uint32_t taddr, const __half *Pc0, size_t vstride, E1Cg cgk,
-                                                 const uint32_t *t_oi, const uint32_t *t_oj, A1Dst dst0, A1Dst dst1,
-                                                 uint32_t x_full, uint32_t parity) {
-  switch (n) {
-#define CB2_E1P_CASE(N) case N: e1_pair_unit<N, HALF>(taddr, Pc0, vstride, cgk, t_oi, t_oj, dst0, dst1, x_full, parity); break;
-    CB2_E1P_CASE(4) CB2_E1P_CASE(5) CB2_E1P_CASE(6) CB2_E1P_CASE(7) CB2_E1P_CASE(8) CB2_E1P_CASE(9) CB2_E1P_CASE(10)
-    CB2_E1P_CASE(11) CB2_E1P_CASE(12) CB2_E1P_CASE(13) CB2_E1P_CASE(14) CB2_E1P_CASE(15) CB2_E1P_CASE(16) CB2_E1P_CASE(17)
-    CB2_E1P_CASE(18) CB2_E1P_CASE(19) CB2_E1P_CASE(20) CB2_E1P_CASE(21) CB2_E1P_CASE(22) CB2_E1P_CASE(23) CB2_E1P_CASE(24)
-#undef CB2_E1P_CASE
-    default: break;   // the caller only comes here for 4 <= n <= CB2_E1_PAIR_MAXN
   }
 }
 

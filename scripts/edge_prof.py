@@ -53,10 +53,8 @@ if os.environ.get("CB2_TIMELINE"):
             print("   G2 stage issue times:", [int(a[itx, 72 + k] - base) for k in range(16)])
             print("   issuer chunk 12: before waits, a_full ok, (w_full ok = chunk time), MMAs issued, commits issued:",
                   [int(a[itx, k] - base) for k in (88, 89, 48 + 12, 90, 91)])
-            print("   E1 tail g0 (local a1) / g1 (remote a1): after bar, after fill, after fence.proxy:",
-                  [int(a[itx, k] - base) for k in (40, 41, 42)], [int(a[itx, k] - base) for k in (44, 45, 46)])
-            print("   E1 (thread 0): entry (P loads issued), x_full ok, first 16 columns done, 64 columns done:",
-                  [int(a[itx, 32 + k] - base) for k in range(4)], "tmem_ld issued, first tmem data:", [int(a[itx, 32 + k] - base) for k in (4, 5)])
+            print("   E1 (thread 0): entry (P loads issued), x_full ok, first 16 columns done, all columns done:",
+                  [int(a[itx, 40 + k] - base) for k in range(4)])
             print("   loader stage 16 (for chunk 16): before w_empty wait, w_empty ok, TMA issued:",
                   [int(a[itx, k] - base) for k in (92, 93, 94)])
     else:
