@@ -25,8 +25,8 @@ int launch_ln_gelu(float *x, const float *g, const float *b, int width, int64_t 
 int launch_film_apply(const float *y, float *h, const float *cond, const int32_t *node2graph, const float *fg,
                       const float *fb, const float *cg, const float *cb, float *hn, int64_t ld_hn, __half *hn16,
                       int64_t ld_hn16, int hn16_kt, int N, int B, int V, cudaStream_t st);
-int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, int64_t rows,
-                     cudaStream_t st);
+int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, const float *w3,
+                     float *out3, int64_t ld3, int64_t rows, cudaStream_t st);
 int launch_validity(const int64_t *a, const float *x, const float *lat, const int32_t *graph_off, int B,
                     const int32_t *target, float max_len, float thr, int32_t *flags, float *min_dist,
                     float *max_abc, cudaStream_t st);
@@ -194,7 +194,15 @@ static int decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_for
   NvtxRange r_heads("cb2:heads");
   float *hf = io->node_features ? io->node_features : w.hf;
   const bool tc_heads = io->precision != CB2_PRECISION_FP32 && m->w_head_t != nullptr;
-  CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, VN, st));
+  if (io->coords_only && tc_heads) {
+    // corrector forward: only pred_x is used (chemeleon.py:440-450).  The three coordinate rows are taken
+    // in fp32 straight from the final LayerNorm's registers: no head GEMM over 104 unused type columns,
+    // no split-precision copy of the features (and no feature store unless the caller wants them).
+    CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, io->node_features, nullptr, m->w_head + (size_t)NTYPE * H,
+                             io->head_out + NTYPE, HEADC, VN, st));
+    return CB2_OK;
+  }
+  CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, nullptr, nullptr, 0, VN, st));
   if (tc_heads) {   // cat16 is dead after the last layer: it carries the hi | lo split of the features
     CB2_TRY(tc_head(m, w.cat16, VN, io->head_out, st));
   } else {

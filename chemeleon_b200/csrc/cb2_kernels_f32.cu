@@ -310,7 +310,8 @@ int launch_film_apply(const float *y, float *h, const float *cond, const int32_t
 // split-precision head GEMM (three fp16 products reproduce the fp32 product to ~2^-22).
 __global__ void __launch_bounds__(256) k_layernorm(const float *__restrict__ x, const float *__restrict__ g,
                                                    const float *__restrict__ b, float *__restrict__ out,
-                                                   __half *__restrict__ split16, int64_t rows) {
+                                                   __half *__restrict__ split16, const float *__restrict__ w3,
+                                                   float *__restrict__ out3, int64_t ld3, int64_t rows) {
   int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -325,12 +326,29 @@ __global__ void __launch_bounds__(256) k_layernorm(const float *__restrict__ x, 
     store_row_half_panel(split16, row, H2, v, lane);
     store_row_half_panel(split16 + (H / 8) * 1024, row, H2, lo, lane);
   }
+  if (w3 != nullptr) {
+    // three-row head on the normalised row, fp32 (coord_out of the corrector forward, cspnet.py:388:
+    // the type logits and the lattice head of that forward are never used, chemeleon.py:440-450)
+    float d[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      float s = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; q4++) {
+        const float4 w = *reinterpret_cast<const float4 *>(w3 + r * H + (lane + 32 * q4) * 4);
+        s = fmaf(v[q4 * 4 + 0], w.x, s); s = fmaf(v[q4 * 4 + 1], w.y, s);
+        s = fmaf(v[q4 * 4 + 2], w.z, s); s = fmaf(v[q4 * 4 + 3], w.w, s);
+      }
+      d[r] = warp_sum(s);
+    }
+    if (lane < 3) out3[row * ld3 + lane] = lane == 0 ? d[0] : lane == 1 ? d[1] : d[2];
+  }
 }
 
-int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, int64_t rows,
-                     cudaStream_t st) {
+int launch_layernorm(const float *x, const float *g, const float *b, float *out, __half *split16, const float *w3,
+                     float *out3, int64_t ld3, int64_t rows, cudaStream_t st) {
   if (rows == 0) return CB2_OK;
-  k_layernorm<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, b, out, split16, rows);
+  k_layernorm<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, b, out, split16, w3, out3, ld3, rows);
   CB2_LAUNCH_OK("k_layernorm");
   return CB2_OK;
 }

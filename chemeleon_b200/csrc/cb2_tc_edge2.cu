@@ -304,7 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       if (leader) mbar_arrive(dst); else mbar_arrive_remote(dst);
     };
 
-    int ri_p = -1, rj_p = 0, ri_t = -1, rj_t = 0, n_f = 0;
+    int ri_p = -1, rj_p = 0, ri_t = -1, rj_t = 0, rj_prev = -1, n_f = 0;
     auto fetch_rows = [&](int item) {
       n_f = g.seg_n[item];
       ri_p = g.row_i[(int64_t)item * 128 + trow];
@@ -312,6 +312,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       if (warp < 4) {
         ri_t = g.row_i[(int64_t)item * 128 + tid];
         rj_t = g.row_j[(int64_t)item * 128 + tid];
+        // node j of the same position in the previous segment: equal = same crystal, its P_j row is already asked for
+        rj_prev = tid >= n_f ? g.row_j[(int64_t)item * 128 + tid - n_f] : -1;
       }
     };
     auto publish_rows = [&](int buf, float (&dl)[3], bool &valid) {
@@ -331,19 +333,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
         tab[buf * 256 + 128 + tid] = oj;
         // crystal of every segment (n >= 4: at most 32 segments): E1 then needs ONE global load for the lattice term
         if (n_f >= 4 && ri_t >= 0 && tid % n_f == 0) tab_g[buf * 32 + tid / n_f] = (uint32_t)g.node2graph[ri_t];
-        // pull the tile's rows of P (both variants) towards L2 long before E1 gathers them; a row of
-        // P_i is shared by the n rows of its segment: only the segment's first row asks for it
+        // pull the tile's rows of P (both variants) towards L2 long before E1 gathers them -- only THIS CTA's
+        // 256 channels (4 of the 8 lines of a half row), a row of P_i once per segment, a row of P_j once per
+        // crystal in the tile
         const int ri_prev = __shfl_up_sync(0xffffffffu, ri_t, 1);
         if (ri_t >= 0) {
 #pragma unroll
           for (int v = 0; v < 2; v++) {
-            const char *pv = reinterpret_cast<const char *>(g.P + (size_t)v * (size_t)g.N * H2);
+            const char *pv = reinterpret_cast<const char *>(g.P + (size_t)v * (size_t)g.N * H2) + 512 * rank;
             if (lane == 0 || ri_prev != ri_t) {
 #pragma unroll
-              for (int l = 0; l < 8; l++) prefetch_l2(pv + (size_t)oi * 2 + l * 128);
+              for (int l = 0; l < 4; l++) prefetch_l2(pv + (size_t)oi * 2 + l * 128);
             }
+            if (rj_prev != rj_t) {
 #pragma unroll
-            for (int l = 0; l < 8; l++) prefetch_l2(pv + (size_t)oj * 2 + l * 128);
+              for (int l = 0; l < 4; l++) prefetch_l2(pv + (size_t)oj * 2 + l * 128);
+            }
           }
         }
       }
