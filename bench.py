@@ -366,9 +366,9 @@ def main():
     e2e = None
     parity = None
     if not args.no_e2e:
-        def e2e_once(seed):
+        def e2e_once(seed, steps=K):
             a, x, l = cdist.sample_sharded(model, nat_global, text_host, null_host, 2.0, 1e-5, seed=seed,
-                                           t_stop=T_STEPS - K)
+                                           t_stop=T_STEPS - steps)
             ha, hx, hl = a.cpu(), x.cpu(), l.cpu()
             atoms = model._to_atoms(ha, hx, hl, nat_global) if rank == 0 else None   # the ase.Atoms boundary
             return ha, hx, hl, atoms
@@ -379,12 +379,27 @@ def main():
         ha, hx, hl, atoms = e2e_once(2)
         ev1.record()
         barrier()
-        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / K)
+        job_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        ms_e2e = job_ms / K
+        # the per-job part (conditioning H2D + projection, initial noise, all-gather, D2H, Atoms objects) is paid once
+        # per 1000-step job, not once per K steps: a 1-timestep job separates it from the per-timestep part
+        barrier()
+        ev0.record()
+        e2e_once(2, 1)
+        ev1.record()
+        barrier()
+        job1_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        fixed_ms = max(0.0, (K * job1_ms - job_ms) / (K - 1)) if K > 1 else 0.0
+        step_ms_e2e = (job_ms - fixed_ms) / K
         h2d = (text_host.numel() + null_host.numel()) * 4 / K
         d2h = (ha.numel() * 8 + hx.numel() * 4 + hl.numel() * 4) / K
         e2e = {"value": Bg / (ms_e2e * 1e-3 * T_STEPS), "unit": "structures/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-               "api": "chemeleon_b200.dist.sample_sharded + state_to_atoms (K-timestep job)"}
+               "api": "chemeleon_b200.dist.sample_sharded + state_to_atoms (K-timestep job)",
+               "per_job_ms": fixed_ms, "per_timestep_ms": step_ms_e2e,
+               "value_1000_step_job": Bg / ((fixed_ms + T_STEPS * step_ms_e2e) * 1e-3),
+               "note": "value = the K-timestep job as measured (per-job costs amortised over K timesteps only); "
+                       "value_1000_step_job = the same costs for the full 1000-timestep job of the metric"}
         # ---- parity at scale / shard invariance: 64 crystals of the job above, re-sampled ALONE on rank 0 ----
         if rank == 0:
             rs = np.random.RandomState(11)

@@ -68,22 +68,38 @@ def symbol_sort_order(numbers: np.ndarray) -> np.ndarray:
     return np.array([i for _, i in deco], dtype=np.int64)
 
 
+# rank of every atomic number in the order of its chemical-symbol STRING (what ase's sort compares)
+_SYMBOL_RANK = np.empty(len(SYMBOLS), dtype=np.int64)
+_SYMBOL_RANK[np.array(sorted(range(len(SYMBOLS)), key=lambda z: SYMBOLS[z]))] = np.arange(len(SYMBOLS))
+
+
+def batch_symbol_order(a: np.ndarray, natoms: Sequence[int]) -> np.ndarray:
+    """`symbol_sort_order` of every crystal of a batch in one vectorised stable sort: global atom
+    indices, crystal by crystal, each crystal's atoms ordered by (symbol string, original index)."""
+    nat = np.asarray(natoms, dtype=np.int64)
+    crystal = np.repeat(np.arange(len(nat)), nat)
+    return np.lexsort((np.arange(a.shape[0]), _SYMBOL_RANK[a], crystal))
+
+
 def state_to_atoms(atom_types: np.ndarray, frac_coords: np.ndarray, lattices: np.ndarray,
                    natoms: Sequence[int]) -> List:
     a = np.where(atom_types <= 103, atom_types, 0)
-    a = np.where(a >= 0, a, 0)
+    a = np.where(a >= 0, a, 0).astype(np.int64)
     out = []
     off = 0
-    lat = lattices.reshape(-1, 3, 3)
-    for i, n in enumerate(natoms):
-        z = a[off:off + n]
-        pos = frac_coords[off:off + n]
-        off += n
-        if HAVE_ASE:  # pragma: no cover
-            at = _AseAtoms(numbers=z, cell=lat[i], pbc=True)
-            at.set_scaled_positions(pos)
+    lat = np.asarray(lattices).reshape(-1, 3, 3)
+    if HAVE_ASE:  # pragma: no cover
+        for i, n in enumerate(natoms):
+            at = _AseAtoms(numbers=a[off:off + n], cell=lat[i], pbc=True)
+            at.set_scaled_positions(frac_coords[off:off + n])
             out.append(_ase_sort(at))
-        else:
-            order = symbol_sort_order(z)
-            out.append(AtomsLite(z[order], lat[i], pos[order]))
+            off += n
+        return out
+    order = batch_symbol_order(a, natoms)
+    z_sorted = a[order]
+    x_sorted = np.asarray(frac_coords, dtype=np.float64)[order]
+    lat = lat.astype(np.float64)
+    for i, n in enumerate(natoms):
+        out.append(AtomsLite(z_sorted[off:off + n], lat[i], x_sorted[off:off + n]))
+        off += n
     return out
