@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, natoms, q):
+def _worker(rank, world, port, natoms, q, precision):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
@@ -24,7 +24,7 @@ def _worker(rank, world, port, natoms, q):
     from chemeleon_b200.weights import random_init_state_dict
 
     sd = random_init_state_dict(SamplerConfig(), seed=2, head_scale=0.01, lattice_identity=True)
-    model = ChemeleonB200(sd, device=f"cuda:{rank}", precision="fp32")
+    model = ChemeleonB200(sd, device=f"cuda:{rank}", precision=precision)
     g = torch.Generator().manual_seed(0)
     B = len(natoms)
     text, null = torch.randn(B, 512, generator=g), torch.randn(1, 512, generator=g)
@@ -34,7 +34,8 @@ def _worker(rank, world, port, natoms, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sampling_matches_single_gpu():
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_two_rank_sampling_matches_single_gpu(precision):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -47,7 +48,8 @@ def test_two_rank_sampling_matches_single_gpu():
     natoms = [5, 12, 7, 7, 3, 9]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29600 + os.getpid() % 1000, natoms, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 1000 + (7 if precision == "tc" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, natoms, q, precision)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -55,7 +57,7 @@ def test_two_rank_sampling_matches_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     sd = random_init_state_dict(SamplerConfig(), seed=2, head_scale=0.01, lattice_identity=True)
-    model = ChemeleonB200(sd, device="cuda:0", precision="fp32")
+    model = ChemeleonB200(sd, device="cuda:0", precision=precision)
     g = torch.Generator().manual_seed(0)
     text, null = torch.randn(len(natoms), 512, generator=g), torch.randn(1, 512, generator=g)
     a1, x1, l1 = sample_sharded(model, natoms, text, null, seed=5, t_stop=994)
