@@ -29,8 +29,10 @@
 //
 //   warps 0-15 : workers.  Embedding group m = warp/2 builds row (warp%2)*32+lane of the chunks with
 //                kc % 8 == m; lane quarter q = warp%4 and (unit, variant) = (warp/8, (warp/4)%2) in E1 / E2
-//   warps 16-19: MMA issue (lane 0, even CTA only), TMEM alloc (warp 16 of both CTAs)
-//   warp 20    : weight loader (lane 0): cp.async.bulk.tensor with cta_group::2, completing on the even
+//   warps 16-17: MMA issue (lane 0, even CTA only; measured: 1 thread 3.84 ms, 2 threads 3.17 ms, 4 threads 3.21 ms
+//                per launch at C3 -- and two fewer warps leave the epilogues 104 registers instead of 96),
+//                TMEM alloc (warp 16 of both CTAs), relay of the odd CTA's a1_rx (warp 16, odd CTA)
+//   warp 18    : weight loader (lane 0): cp.async.bulk.tensor with cta_group::2, completing on the even
 //                CTA's barrier
 #include <cuda.h>
 
@@ -65,7 +67,7 @@ constexpr int T2_BAR_OFF = T2_W_OFF + T2_WSTAGES * T2_W_BYTES;
 constexpr int T2_TAB_OFF = T2_BAR_OFF + 512;              // 2 buffers x (off_i[128], off_j[128]) uint32
 constexpr int T2_SEG_OFF = T2_TAB_OFF + 2 * 1024;          // 2 buffers x crystal of each segment [32] (tiles with n >= 4)
 constexpr int T2_SMEM = T2_SEG_OFF + 2 * 128;
-constexpr int T2_NISSUE = 4;                              // MMA-issuing threads; must divide T2_WSTAGES and T2_ESLOTS (see below)
+constexpr int T2_NISSUE = 2;                              // MMA-issuing threads; must divide T2_WSTAGES and T2_ESLOTS (see below)
 constexpr int T2_WORKERS = 512;
 constexpr int T2_THREADS = T2_WORKERS + 32 * (T2_NISSUE + 1);
 constexpr int T2_NCH1 = DIS / 32;                         // 24 GEMM1 chunks of K = 32
@@ -231,7 +233,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
         umma2_commit_mc(x_full, (uint16_t)3);
         if (ii == 0) T2_STAMP(2);
         // GEMM2: O_o += W2[o] [a1^0 | a1^1]^T  (the units hold b2).  O1 -- the unit that aliases X -- goes first:
-        // its E2 and re-initialisation then overlap GEMM2 of O0, and the next tile's GEMM1 starts at once
+        // its E2 and re-initialisation then overlap GEMM2 of O0, and the next tile's GEMM1 starts at once.
+        // (Tried: swapping the roles of the two TMEM halves from tile to tile with O0 first, so that GEMM1 never
+        // waits for the epilogue of the last unit -- with and without moving the embedding production to the
+        // warps that are free then: 3.42 / 3.47 ms per launch at C3 against 3.17 ms, faster only for n = 6.)
         mbar_wait_spin(a1_rx, it & 1);                 // this CTA: workers through E1, the peer's half of a1 has landed
         mbar_wait_spin(a1_peer, it & 1);               // ... and the same in the odd CTA
         if (ii == 0) T2_STAMP(3);
