@@ -39,8 +39,10 @@ def _deps():
 
 
 def source_hash() -> str:
-    """Content hash of everything the library is built from (file mtimes do not survive a copy of the tree)."""
-    h = hashlib.sha256(" ".join(NVCC_FLAGS + [os.environ.get("CB2_NVCC_EXTRA", "")]).encode())
+    """Content hash of everything the library is built from (file mtimes do not survive a copy of the tree).
+    CB2_NVCC_EXTRA (development builds, e.g. -DCB2_EDGE_TIMELINE) is deliberately not part of it: such a
+    library is built with --force and must not be rebuilt by the next process that has a clean environment."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for d in _deps():
         h.update(os.path.basename(d).encode())
         with open(d, "rb") as f:

@@ -205,17 +205,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
         mbar_wait_spin(x_free, it & 1);
         tc_fence_after_sync();
         if (ii == 0) T2_STAMP(1);
-        // GEMM1: X_u += W_fd[u] emb^T  (the units were cleared by the workers)
+        // GEMM1: X_u += W_fd[u] emb^T  (the units were cleared by the workers).  The barrier probes of this
+        // thread's NEXT chunk are fired before the MMAs of the current one (see mbar_test).
+        auto g1_pa = [&](int kc) { return (it * 3 + kc / T2_ESLOTS) & 1; };
+        auto g1_pw = [&](int kc) { return t2_w_use(kc % T2_WRING1, it, kc / T2_WRING1) & 1; };
+        bool ra = mbar_test(a_full(ii % T2_ESLOTS), g1_pa(ii)), rw = mbar_test(w_full(ii % T2_WRING1), g1_pw(ii));
 #pragma unroll
         for (int kc = 0; kc < T2_NCH1; kc++) {
           if (kc % T2_NISSUE != ii) continue;
           const int as = kc % T2_ESLOTS, ws = kc % T2_WRING1;
           if (kc == 12) T2_STAMP(88);
-          mbar_wait_spin(a_full(as), (it * 3 + kc / T2_ESLOTS) & 1);
+          if (!ra) mbar_wait_spin(a_full(as), g1_pa(kc));
           if (kc == 12) T2_STAMP(89);
-          mbar_wait_spin(w_full(ws), t2_w_use(ws, it, kc / T2_WRING1) & 1);
+          if (!rw) mbar_wait_spin(w_full(ws), g1_pw(kc));
           tc_fence_after_sync();
           T2_STAMP(48 + kc);
+          const int kn = kc + T2_NISSUE;
+          if (kn < T2_NCH1) {
+            ra = mbar_test(a_full(kn % T2_ESLOTS), g1_pa(kn));
+            rw = mbar_test(w_full(kn % T2_WRING1), g1_pw(kn));
+          }
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             const uint64_t bd = d_e + (uint64_t)((T2_E_OFF + as * T2_E_BYTES + 2 * j * 1024) >> 4);
@@ -244,13 +253,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
         fence_proxy_async_smem();                      // a1 bytes written by st.async -> async proxy (the MMA reads them)
         tc_fence_after_sync();
         if (ii == 0) T2_STAMP(4);
+        auto g2_pw = [&](int s2) { return t2_w_use(s2 % T2_WSTAGES, it, T2_NCH1 / T2_WRING1 + s2 / T2_WSTAGES) & 1; };
+        rw = mbar_test(w_full(ii % T2_WSTAGES), g2_pw(ii));
 #pragma unroll
         for (int s2 = 0; s2 < T2_NST2; s2++) {
           if (s2 % T2_NISSUE != ii) continue;
           const int o = 1 - (s2 >> 3), s = s2 & 7, ws = s2 % T2_WSTAGES;   // O1 (aliases X) first
-          mbar_wait_spin(w_full(ws), t2_w_use(ws, it, T2_NCH1 / T2_WRING1 + s2 / T2_WSTAGES) & 1);
+          if (!rw) mbar_wait_spin(w_full(ws), g2_pw(s2));
           tc_fence_after_sync();
           T2_STAMP(72 + s2);
+          if (s2 + T2_NISSUE < T2_NST2) rw = mbar_test(w_full((s2 + T2_NISSUE) % T2_WSTAGES), g2_pw(s2 + T2_NISSUE));
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint64_t ad = d_2k + (uint64_t)((t2_w_off(ws) + 2 * j * 2048) >> 4);
