@@ -94,6 +94,15 @@ __host__ __device__ constexpr uint32_t t2_w_use(int st, uint32_t it, int u) {
 
 #define T2_WORKER_BARRIER() asm volatile("bar.sync 1, 512;" ::: "memory")
 
+// sin / cos of 2 pi t: exact range reduction to [-1/2, 1/2] turns, then the MUFU approximations (absolute error
+// 2^-21 there; the 16-step rotation recurrence that follows amplifies it linearly, far below the fp16 rounding
+// of the embedding).  sincospif costs ~100 instructions per call and the producers sit on GEMM1's critical path.
+__device__ __forceinline__ void sincos_turns(float t, float &s, float &c) {
+  const float a = (t - rintf(t)) * 6.283185307179586f;
+  s = __sinf(a);
+  c = __cosf(a);
+}
+
 // development aid: timeline of cluster 0's even CTA, tiles 1..3 (clock64 stamps), read back by cb2_debug_edge_timeline()
 #ifndef CB2_EDGE_TIMELINE
 __device__ long long g_edge2_dbg[3 * 96];
@@ -375,8 +384,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
     auto produce = [&](int d, const float (&dl)[3], bool valid, uint32_t tile_it) {
       const uint32_t use = tile_it * 3 + d;
       float s1, c1r, sk, ck;
-      sincospif(2.0f * dl[d], &s1, &c1r);
-      sincospif((float)(32 * m8) * dl[d], &sk, &ck);
+      sincos_turns(dl[d], s1, c1r);                          // rotation by one frequency step: angle 2 pi dl
+      sincos_turns((float)(16 * m8) * dl[d], sk, ck);        // first frequency of this chunk: 16 m8
       mbar_wait(a_empty(m8), (use & 1) ^ 1);
       uint8_t *slot = smem + T2_E_OFF + m8 * T2_E_BYTES + prow * 16;
 #pragma unroll
