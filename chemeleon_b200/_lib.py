@@ -20,6 +20,7 @@ TILE_ROWS = 128
 PRECISION_FP32 = 0
 PRECISION_TC_F16 = 1
 MODEL_EDGE_SINGLE_CTA = 1
+MODEL_NODE_UNFUSED = 2
 PACK_KMAJOR, PACK_FD, PACK_ROW_BLOCKS, PACK_HEAD_SPLIT = 0, 1, 2, 3
 FLAG_NONFINITE = 1
 FLAG_TC_RANGE = 2

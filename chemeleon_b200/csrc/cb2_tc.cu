@@ -349,21 +349,52 @@ int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_o
   return launch_tc_linear(a, st);
 }
 
-// One CSPNet trunk pass on the tensor cores.  fp32 row-major: h (residual stream), y, P;
+int launch_tc_node2(const cb2_model *m, const cb2_layer_weights *Lmlp, const cb2_layer_weights *Lfilm,
+                    const cb2_batch *b, const float *film_cond, float *h, const __half *h16, __half *cat16, __half *P,
+                    int n_sm, cudaStream_t st);
+
+// One CSPNet trunk pass on the tensor cores.  fp32 row-major: h (residual stream); fp16 row-major: P;
 // fp16 row-panel: h16, cat16 = [LN(h) | agg], z16.
+//
+// Default (FiLM conditioning present): 2 launches per layer -- the edge kernel and ONE node-chain kernel
+// k_tc_node2 per layer boundary (node MLP of layer l -> FiLM block, LayerNorm and hoist GEMM of layer l+1).
+// cb2_model.flags & CB2_MODEL_NODE_UNFUSED (and forwards without FiLM) take round 1's four kernels per layer.
 int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_io *io, ForwardWs &w,
                       cudaStream_t st) {
   const int N = b->n_nodes, B = b->n_graphs, V = b->n_variants;
   const int64_t VN = (int64_t)V * N;
   if (!m->film_wp_t) return fail(CB2_ERR_BAD_ARG, "tensor-core path needs the fp16 operand images (pack with tensor_core=True)");
-  if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
-  int sms = 0;
-  CB2_TRY(num_sms(&sms));
-  CB2_TRY(launch_lattice_ip(io->lattices, m, w.cg, B, io->flags, st));      // all layers' lattice terms, one launch
   for (int li = 0; li < m->n_layers; li++) {
     const cb2_layer_weights &L = m->layers[li];
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
+  }
+  if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
+  int sms = 0;
+  CB2_TRY(num_sms(&sms));
+  CB2_TRY(launch_lattice_ip(io->lattices, m, w.cg, B, io->flags, st));      // all layers' lattice terms, one launch
+  __half *P16 = reinterpret_cast<__half *>(w.P);
+  const bool chain = io->film_cond != nullptr && !(m->flags & CB2_MODEL_NODE_UNFUSED);
+  if (chain) {
+    {
+      NvtxRange r("cb2:node_chain(head)");
+      CB2_TRY(launch_tc_node2(m, nullptr, &m->layers[0], b, io->film_cond, w.h, w.h16, w.cat16, P16, sms, st));
+    }
+    for (int li = 0; li < m->n_layers; li++) {
+      const cb2_layer_weights &L = m->layers[li];
+      NvtxRange r_layer("cb2:csp_layer");
+      {
+        NvtxRange r("cb2:edge");
+        CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, P16, w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
+      }
+      NvtxRange r("cb2:node_chain");
+      CB2_TRY(launch_tc_node2(m, &L, li + 1 < m->n_layers ? &m->layers[li + 1] : nullptr, b, io->film_cond, w.h,
+                              w.h16, w.cat16, P16, sms, st));
+    }
+    return CB2_OK;
+  }
+  for (int li = 0; li < m->n_layers; li++) {
+    const cb2_layer_weights &L = m->layers[li];
     NvtxRange r_layer("cb2:csp_layer");
     if (io->film_cond != nullptr) {
       // FiLM projection + LN + FiLM + SiLU + residual + layer LN in one kernel (y stays in TMEM)
@@ -377,13 +408,12 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
       NvtxRange r("cb2:hoist");
       TcLinearArgs a{};   // P = hn [W_hi;W_hj]^T in fp16; the per-crystal lattice term stays in fp32 (cg)
       a.A = w.cat16; a.a_kt = H2; a.M = VN; a.K = H; a.Wt = (const __half *)L.w_hij_t; a.Nw = H2;
-      a.C16r = reinterpret_cast<__half *>(w.P); a.ldc16r = H2;
+      a.C16r = P16; a.ldc16r = H2;
       CB2_TRY(launch_tc_linear(a, st));
     }
     {
       NvtxRange r("cb2:edge");
-      CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, reinterpret_cast<const __half *>(w.P),
-                            w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
+      CB2_TRY(tc_edge_layer(m, L, b, io->frac_coords, P16, w.cg + (size_t)li * B * H, w.cat16, 0, H, H2, st));
     }
     {
       NvtxRange r("cb2:node_mlp");

@@ -48,6 +48,7 @@ __device__ int g_edge2_it;
   } while (0)
 #endif
 #include "cb2_tc_edge_epi.cuh"
+#include "cb2_tmap.cuh"
 
 namespace cb2 {
 
@@ -495,8 +496,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_weight_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t k8, uint32_t box_rows,
-                             uint32_t box_k8) {
+int encode_tensor_map_3d(CUtensorMap *tm, const void *base, const uint64_t (&dims_)[3], const uint64_t (&strides_)[2],
+                         const uint32_t (&box_)[3]) {
   // resolved once; the driver entry point does not depend on the device (no per-process configuration)
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
@@ -507,17 +508,22 @@ static int encode_weight_map(CUtensorMap *tm, const void *base, uint64_t rows, u
       return fail(CB2_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     fn = reinterpret_cast<PFN_encodeTiled>(p);
   }
-  // fp16 image [k8][rows][8] seen as [k8][rows / 32][256 halves]: a 512-byte innermost dimension (the
-  // largest a box allows) instead of the natural 16-byte one, which would cost one request per row
-  const cuuint64_t dims[3] = {256, rows / 32, k8};
-  const cuuint64_t strides[2] = {512, rows * 16};
-  const cuuint32_t box[3] = {256, box_rows / 32, box_k8};
+  const cuuint64_t dims[3] = {dims_[0], dims_[1], dims_[2]};
+  const cuuint64_t strides[2] = {strides_[0], strides_[1]};
+  const cuuint32_t box[3] = {box_[0], box_[1], box_[2]};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CB2_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return CB2_OK;
+}
+
+int encode_weight_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t k8, uint32_t box_rows,
+                      uint32_t box_k8) {
+  // fp16 image [k8][rows][8] seen as [k8][rows / 32][256 halves]: a 512-byte innermost dimension (the
+  // largest a box allows) instead of the natural 16-byte one, which would cost one request per row
+  return encode_tensor_map_3d(tm, base, {256, rows / 32, k8}, {512, rows * 16}, {256, box_rows / 32, box_k8});
 }
 
 int launch_tc_edge2(const TcEdgeArgs &a, int n_sm, cudaStream_t st) {

@@ -102,6 +102,8 @@ typedef struct {
 /* cb2_model.flags */
 #define CB2_MODEL_EDGE_SINGLE_CTA 1  /* V == 2: run the one-CTA edge kernel per variant instead of the CTA-pair
                                       * kernel that shares the sinusoid GEMM between the variants (A/B testing) */
+#define CB2_MODEL_NODE_UNFUSED 2     /* run the node-level GEMMs of a layer as four kernels (FiLM block, hoist GEMM, node
+                                      * MLP x 2) instead of the one CTA-pair chain kernel per layer boundary (A/B testing) */
 
 /* ---- topology of one ragged batch; fixed for a whole sampling run ----
  * Replaces CSPNet.gen_edges (cspnet.py:319-324): edges are implied by the

@@ -148,3 +148,43 @@ def test_edge_pair_kernel_is_repeatable():
             bad = (a - r).abs() > 2.5e-3 * r.abs() + 2e-4         # 2 fp16 ulps (+ an absolute floor near zero)
             assert int(bad.sum()) == 0, f"{int(bad.sum())} outputs differ by more than 2 fp16 ulps"
     print(f"pair kernel repeatability: {n_diff} of {11 * ref.numel()} fp16 outputs differ in their last bits, none by more than 2 ulps")
+
+
+@pytest.mark.parametrize("natoms,layers,coords_only", [([6, 6, 6], 2, False), ([20] * 7, 1, False),
+                                                      ([4, 7, 5, 1, 40, 33], 3, True), ([20] * 300 + [33] * 5, 6, False),
+                                                      ([40] * 150 + [13] * 5 + [64, 3], 2, False)])
+def test_node_chain_kernel_matches_unfused_kernels(natoms, layers, coords_only):
+    """The CTA-pair node-chain kernel (k_tc_node2: node MLP -> FiLM block -> LayerNorm -> hoist GEMM per layer
+    boundary, activations resident in shared memory, cta_group::2) against round 1's four kernels per layer
+    (k_tc_film + 3 x k_tc_linear, selected with cb2_model.flags): same fp16 operands, same K order, same
+    epilogue arithmetic -- decoder outputs agree to fp32 accumulation noise.  Covers 1 panel (phantom peer
+    panel), odd panel counts, partial last panels, 1 / 2 / 3 / 6 layers (HEAD + TAIL only, with FULL links)
+    and several work items per cluster; each forward is run twice (the second starts from the first's TMEM / smem)."""
+    from chemeleon_b200 import _lib
+    from chemeleon_b200.config import SamplerConfig
+    from chemeleon_b200.engine import DecoderEngine
+    from chemeleon_b200.weights import random_init_state_dict
+
+    cfg = SamplerConfig(num_layers=layers)
+    eng = DecoderEngine(random_init_state_dict(cfg, seed=11), cfg, precision="tc")
+    topo = eng.topology(natoms, 2)
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(1, 90, (topo.N,), generator=g).cuda()
+    x = torch.rand(topo.N, 3, generator=g).cuda()
+    l = (torch.randn(topo.B, 3, 3, generator=g) * 0.3 + 4 * torch.eye(3)).reshape(topo.B, 9).cuda()
+    cond = torch.nn.functional.silu(torch.randn(2 * topo.B, 1024, generator=g)).cuda()
+    outs = []
+    for flags in (_lib.MODEL_NODE_UNFUSED, 0):
+        eng.model.flags = flags
+        for _ in range(2):
+            head, lat, feat = eng.forward(topo, a, x, l, cond, coords_only=coords_only)
+        torch.cuda.synchronize()
+        assert torch.isfinite(head[:, 104:107]).all() and torch.isfinite(feat).all()
+        outs.append((head.cpu(), lat.cpu(), feat.cpu()))
+    e_feat = rel_err(outs[1][2], outs[0][2])
+    e_x = rel_err(outs[1][0][:, 104:107], outs[0][0][:, 104:107])
+    print(f"node chain vs unfused: features {e_feat:.2e}, coords {e_x:.2e}")
+    assert e_feat < 2e-4 and e_x < 2e-4
+    if not coords_only:
+        assert rel_err(outs[1][0][:, :104], outs[0][0][:, :104]) < 2e-4
+        assert rel_err(outs[1][1], outs[0][1]) < 2e-4
