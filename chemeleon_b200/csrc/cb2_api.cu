@@ -19,6 +19,8 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 // launchers from the other translation units
 int launch_embed(const int64_t *a, const float *emb, float *h, int N, int V, cudaStream_t st);
+int launch_embed_panels(const int64_t *a, const float *emb, float *hp, __half *h16, int N, int V, cudaStream_t st);
+bool tc_uses_node_chain(const cb2_model *m, const cb2_forward_io *io);
 int launch_film_cond(const float *time_table, const float *text_part, const int32_t *text_row, const int32_t *t_dev,
                      float *out, int64_t rows, cudaStream_t st);
 int launch_ln_gelu(float *x, const float *g, const float *b, int width, int64_t rows, cudaStream_t st);
@@ -52,13 +54,14 @@ int tc_linear_simple(const void *A16, int64_t lda, const void *Wt, int Nw, const
                      int64_t ldc, int64_t M, int K, int silu, void *workspace, size_t workspace_bytes, cudaStream_t st);
 int debug_edge_timeline(long long *out96);
 int debug_edge2_timeline(long long *out96x3);
+int debug_node2_timeline(long long *out64x3);
 int tc_edge_layer(const cb2_model *m, const cb2_layer_weights &L, const cb2_batch *b, const float *x, const __half *P,
                   const float *cg, __half *agg16, int64_t ld_agg, int agg_col, int agg_kt, cudaStream_t st);
 
 size_t carve_forward(Arena &a, const cb2_batch *b, int n_layers, int precision, ForwardWs &w) {
   const size_t VN = (size_t)b->n_variants * b->n_nodes;
   w = ForwardWs{};
-  w.h = a.take<float>(VN * H);
+  w.h = a.take<float>((precision == CB2_PRECISION_FP32 ? VN : (VN + 127) / 128 * 128) * H);
   w.hf = a.take<float>(VN * H);
   w.cg = a.take<float>((size_t)n_layers * b->n_graphs * H);
   if (precision == CB2_PRECISION_FP32) {
@@ -185,24 +188,29 @@ static int decoder_forward(const cb2_model *m, const cb2_batch *b, const cb2_for
   const int64_t VN = (int64_t)V * N;
   if (N == 0) return CB2_OK;
   NvtxRange r_fwd(io->coords_only ? "cb2:forward(corrector)" : "cb2:forward(predictor)");
-  CB2_TRY(launch_embed(io->atom_types, m->emb, w.h, N, V, st));
+  w.h_final = nullptr;
+  if (io->precision != CB2_PRECISION_FP32 && tc_uses_node_chain(m, io))
+    CB2_TRY(launch_embed_panels(io->atom_types, m->emb, w.h, w.h16, N, V, st));   // h, h16 in the chain kernel's layouts
+  else
+    CB2_TRY(launch_embed(io->atom_types, m->emb, w.h, N, V, st));
   if (io->precision == CB2_PRECISION_FP32) {
     CB2_TRY(f32_forward_layers(m, b, io, w, st));
   } else {
     CB2_TRY(tc_forward_layers(m, b, io, w, st));
   }
   NvtxRange r_heads("cb2:heads");
+  const float *h_last = w.h_final ? w.h_final : w.h;
   float *hf = io->node_features ? io->node_features : w.hf;
   const bool tc_heads = io->precision != CB2_PRECISION_FP32 && m->w_head_t != nullptr;
   if (io->coords_only && tc_heads) {
     // corrector forward: only pred_x is used (chemeleon.py:440-450).  The three coordinate rows are taken
     // in fp32 straight from the final LayerNorm's registers: no head GEMM over 104 unused type columns,
     // no split-precision copy of the features (and no feature store unless the caller wants them).
-    CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, io->node_features, nullptr, m->w_head + (size_t)NTYPE * H,
+    CB2_TRY(launch_layernorm(h_last, m->final_g, m->final_b, io->node_features, nullptr, m->w_head + (size_t)NTYPE * H,
                              io->head_out + NTYPE, HEADC, VN, st));
     return CB2_OK;
   }
-  CB2_TRY(launch_layernorm(w.h, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, nullptr, nullptr, 0, VN, st));
+  CB2_TRY(launch_layernorm(h_last, m->final_g, m->final_b, hf, tc_heads ? w.cat16 : nullptr, nullptr, nullptr, 0, VN, st));
   if (tc_heads) {   // cat16 is dead after the last layer: it carries the hi | lo split of the features
     CB2_TRY(tc_head(m, w.cat16, VN, io->head_out, st));
   } else {
@@ -243,6 +251,7 @@ int cb2_validity_filter(const int64_t *atom_types, const float *frac_coords, con
 /* development aid (not part of the documented ABI): clock64 timeline of the edge kernel's CTA 0 */
 int cb2_debug_edge_timeline(long long *out96) { return debug_edge_timeline(out96); }
 int cb2_debug_edge2_timeline(long long *out96x3) { return debug_edge2_timeline(out96x3); }
+int cb2_debug_node2_timeline(long long *out64x3) { return debug_node2_timeline(out64x3); }
 
 int cb2_check_device(int device) {
   cudaDeviceProp prop;

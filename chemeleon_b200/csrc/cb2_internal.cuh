@@ -74,7 +74,8 @@ struct Arena {
 
 // Buffers of one decoder forward (all row-major fp32 unless noted).
 struct ForwardWs {
-  float *h;       // [VN,512] residual stream
+  float *h;       // [VN,512] residual stream (tensor-core node-chain path: panel layout, whole panels of 128 rows)
+  float *h_final; // where the trunk left the final h, row-major (NULL = h)
   float *y;       // [VN,512] FiLM projection / scratch
   float *cat;     // [VN,1024] cols 0:512 = LN(h) (hn), 512:1024 = aggregated edge features
   float *P;       // [VN,1024] hoisted edge-MLP terms P_i | P_j = hn [W_hi;W_hj]^T (fp16 on the tensor-core path);

@@ -23,6 +23,37 @@ __global__ void k_embed(const int64_t *__restrict__ a, const float *__restrict__
   reinterpret_cast<float4 *>(h)[idx] = reinterpret_cast<const float4 *>(emb)[(int64_t)t * (H / 4) + c4];
 }
 
+// ... into the panel layouts of the node-chain kernel (cb2_tc_node2.cu): fp32 [panel][128 c4][128 rows][4] and the
+// fp16 operand copy [panel][64 k8][128 rows][8]; a thread = (row, k8), rows past V*N are zero-filled
+__global__ void k_embed_panels(const int64_t *__restrict__ a, const float *__restrict__ emb, float *__restrict__ hp,
+                               __half *__restrict__ h16, int N, int V) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // [panel][k8][row]
+  const int64_t rows = (int64_t)V * N, rows_p = (rows + 127) / 128 * 128;
+  if (idx >= rows_p * (H / 8)) return;
+  const int r = (int)(idx % 128), k8 = (int)((idx / 128) % (H / 8));
+  const int64_t panel = idx / (128 * (H / 8)), row = panel * 128 + r;
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+  if (row < rows) {
+    long long t = a[row % N];
+    if (t < 0 || t >= NTYPE) t = 0;
+    lo = reinterpret_cast<const float4 *>(emb)[(int64_t)t * (H / 4) + 2 * k8];
+    hi = reinterpret_cast<const float4 *>(emb)[(int64_t)t * (H / 4) + 2 * k8 + 1];
+  }
+  float4 *dst = reinterpret_cast<float4 *>(hp) + panel * (128 * 128) + (2 * k8) * 128 + r;
+  dst[0] = lo;
+  dst[128] = hi;
+  reinterpret_cast<uint4 *>(h16)[idx] =
+      make_uint4(pack_half2_sat(lo.x, lo.y), pack_half2_sat(lo.z, lo.w), pack_half2_sat(hi.x, hi.y), pack_half2_sat(hi.z, hi.w));
+}
+
+int launch_embed_panels(const int64_t *a, const float *emb, float *hp, __half *h16, int N, int V, cudaStream_t st) {
+  const int64_t rows_p = ((int64_t)V * N + 127) / 128 * 128, total = rows_p * (H / 8);
+  if (total == 0) return CB2_OK;
+  k_embed_panels<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, emb, hp, h16, N, V);
+  CB2_LAUNCH_OK("k_embed_panels");
+  return CB2_OK;
+}
+
 int launch_embed(const int64_t *a, const float *emb, float *h, int N, int V, cudaStream_t st) {
   int64_t total = (int64_t)V * N * (H / 4);
   if (total == 0) return CB2_OK;

@@ -350,8 +350,12 @@ int tc_head(const cb2_model *m, const __half *split16, int64_t VN, float *head_o
 }
 
 int launch_tc_node2(const cb2_model *m, const cb2_layer_weights *Lmlp, const cb2_layer_weights *Lfilm,
-                    const cb2_batch *b, const float *film_cond, float *h, const __half *h16, __half *cat16, __half *P,
-                    int n_sm, cudaStream_t st);
+                    const cb2_batch *b, const float *film_cond, float *h, float *h_rowmajor, const __half *h16,
+                    __half *cat16, __half *P, int n_sm, cudaStream_t st);
+
+bool tc_uses_node_chain(const cb2_model *m, const cb2_forward_io *io) {
+  return io->film_cond != nullptr && !(m->flags & CB2_MODEL_NODE_UNFUSED);
+}
 
 // One CSPNet trunk pass on the tensor cores.  fp32 row-major: h (residual stream); fp16 row-major: P;
 // fp16 row-panel: h16, cat16 = [LN(h) | agg], z16.
@@ -369,16 +373,16 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
     if (!L.w_hij_t || !L.w_fd_t || !L.w2_t || !L.wn1_t || !L.wn2_t)
       return fail(CB2_ERR_BAD_ARG, "tensor-core path: layer operand image missing");
   }
-  if (io->film_cond != nullptr) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
+  const bool chain = tc_uses_node_chain(m, io);   // then h / h16 arrive in the panel layouts (k_embed_panels)
+  if (io->film_cond != nullptr && !chain) CB2_TRY(launch_to_panels<float>(w.h, H, w.h16, VN, H, H, 0, st));
   int sms = 0;
   CB2_TRY(num_sms(&sms));
   CB2_TRY(launch_lattice_ip(io->lattices, m, w.cg, B, io->flags, st));      // all layers' lattice terms, one launch
   __half *P16 = reinterpret_cast<__half *>(w.P);
-  const bool chain = io->film_cond != nullptr && !(m->flags & CB2_MODEL_NODE_UNFUSED);
   if (chain) {
     {
       NvtxRange r("cb2:node_chain(head)");
-      CB2_TRY(launch_tc_node2(m, nullptr, &m->layers[0], b, io->film_cond, w.h, w.h16, w.cat16, P16, sms, st));
+      CB2_TRY(launch_tc_node2(m, nullptr, &m->layers[0], b, io->film_cond, w.h, nullptr, w.h16, w.cat16, P16, sms, st));
     }
     for (int li = 0; li < m->n_layers; li++) {
       const cb2_layer_weights &L = m->layers[li];
@@ -389,8 +393,9 @@ int tc_forward_layers(const cb2_model *m, const cb2_batch *b, const cb2_forward_
       }
       NvtxRange r("cb2:node_chain");
       CB2_TRY(launch_tc_node2(m, &L, li + 1 < m->n_layers ? &m->layers[li + 1] : nullptr, b, io->film_cond, w.h,
-                              w.h16, w.cat16, P16, sms, st));
+                              w.P, w.h16, w.cat16, P16, sms, st));
     }
+    w.h_final = w.P;          // mode TAIL wrote the final h row-major, fp32, over P (dead after the last edge kernel)
     return CB2_OK;
   }
   for (int li = 0; li < m->n_layers; li++) {

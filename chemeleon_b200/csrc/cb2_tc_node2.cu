@@ -49,6 +49,25 @@ constexpr int N2_SMEM = N2_BAR_OFF + 512;
 constexpr int N2_THREADS = 32 * 18;
 static_assert(N2_SMEM <= 232448, "shared memory budget");
 
+// development aid: clock64 timeline of cluster 0's even CTA (MMA thread and epilogue warp 2), panels 1..3 of a
+// FULL launch; read back by cb2_debug_node2_timeline()
+__device__ long long g_node2_dbg[3 * 64];
+#ifdef CB2_NODE_TIMELINE
+#define N2_STAMP(itv, slot)                                                                    \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && g.do_mlp && g.do_film && (itv) >= 1 && (itv) <= 3)                  \
+      g_node2_dbg[((itv) - 1) * 64 + (slot)] = clock64();                                      \
+  } while (0)
+#else
+#define N2_STAMP(itv, slot) do { } while (0)
+#endif
+
+#ifdef N2_EXP_NO_COND
+#define N2_COND(p) make_float4(1.f, 1.f, 1.f, 1.f)
+#else
+#define N2_COND(p) __ldg(reinterpret_cast<const float4 *>(p))
+#endif
+
 struct TcNodeArgs {
   int64_t M;               // V * N rows
   int n_pairs;             // pairs of 128-row panels
@@ -60,25 +79,56 @@ struct TcNodeArgs {
   const float *cond;       // [V*B,1024] scale | shift
   const int32_t *node2graph;
   int N, B;
-  float *h;                // [M,512] residual stream, fp32 row-major, in place
+  float *h;                // residual stream, fp32 in the PANEL layout [panel][128 c4][128 rows][4 floats], in place: a
+                           // thread owns a row, so its 16-byte pieces are coalesced across the warp (a row-major h
+                           // costs one 128-byte line per thread and access: measured 28 k cycles for E2 instead of 8 k)
+  float *h_rowmajor;       // mode TAIL: the new h goes HERE, [M,512] row-major, for the final LayerNorm (not to h)
   __half *cat16;           // row-panel, 1024 columns per panel: columns 0:512 <- LN_layer(h)
   __half *P;               // [M,1024] fp16 row-major hoisted edge terms
 };
 
-// 32-byte global accesses: a thread owns a row, so consecutive lanes are 2 KB apart -- a 256-bit access is one
-// whole sector per thread (16-byte accesses would fetch / write every sector twice)
-__device__ __forceinline__ void ld_f8_stream(const float *p, float (&v)[8]) {
-  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+// 32-byte global stores for row-major outputs (P, the final h): a thread owns a row, so consecutive lanes are
+// 1-2 KB apart -- a 256-bit access is one whole sector per thread
+__device__ __forceinline__ float4 ld_f4_stream(const float *p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
+  return v;
+}
+// Per-column parameters (biases, LayerNorm affine terms: 14 KB, read by every thread for every row): kept in the
+// ~24 KB of L1 that 227 KB of shared memory leave, by making them the ONLY global data that allocates there
+// (ncu before: L1 hit rate 12 %, long-scoreboard stalls on these loads in every epilogue block)
+__device__ __forceinline__ float4 ld_param4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// read-only data that must not displace them (the FiLM row of the thread's crystal: ~100 KB per panel)
+__device__ __forceinline__ float4 ld_nc_f4_stream(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_f4_stream(float *p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_u4_stream(void *p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ void st_f8(float *p, const float (&v)[8]) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
 __device__ __forceinline__ void st_u8(void *p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
@@ -119,6 +169,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
     tmem_alloc2(smem_u32(tmem_slot), 512);
     tmem_relinquish2();
   }
+#ifdef N2_STAGGER
+  // experiment: start the clusters out of phase so that their memory-heavy and tensor-heavy phases interleave
+  if (warp == 0) {
+    const long long t0 = clock64(), d = (long long)(cl & 3) * N2_STAGGER;
+    while (clock64() - t0 < d) { }
+  }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();               // the peer's barriers are initialised before anybody arrives on them
@@ -234,11 +291,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           if (g.do_film) { wait_half(0, 1); wait_half(1, 1); } else wait_x();
           tc_fence_after_sync();
         }
+        N2_STAMP(it, 0);
         if (g.do_mlp) {
           gemm512(16, true);                    // G1
+          N2_STAMP(it, 1);
           wait_x();                             // E1: X = z
+          N2_STAMP(it, 2);
           tc_fence_after_sync();
           gemm512(8, false);                    // G2
+          N2_STAMP(it, 3);
           if (!g.do_film) umma2_commit_mc(x_dead, (uint16_t)3);
         }
         if (g.do_film) {
@@ -246,8 +307,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             wait_x();                           // E2: X = h16
             tc_fence_after_sync();
           }
+          N2_STAMP(it, 4);
           gemm512(8, !g.do_mlp);                // G3 (mode HEAD: X arrives through the A ring)
+          N2_STAMP(it, 5);
           wait_x();                             // E3: X = hn
+          N2_STAMP(it, 6);
           tc_fence_after_sync();
           for (int u = 0; u < 4; u++) {         // G4: four units of 256 columns, alternating TMEM halves
             const int hf = u & 1;
@@ -263,6 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
               done_w();
             }
             umma2_commit_mc(acc_full(hf), (uint16_t)3);
+            N2_STAMP(it, 7 + u);
           }
           umma2_commit_mc(x_dead, (uint16_t)3);
         }
@@ -288,16 +353,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
       }
     };
     uint32_t n_all = 0;
+#ifdef CB2_NODE_TIMELINE
+    uint32_t eit = 0;
+#define N2_ESTAMP(slot) do { if (warp == 2 && lane == 0) N2_STAMP(eit, slot); } while (0)
+#else
+#define N2_ESTAMP(slot) do { } while (0)
+#endif
     for (int pp = cl; pp < g.n_pairs; pp += n_cl) {
       const int panel = 2 * pp + (int)rank;
       const int64_t grow = (int64_t)panel * 128 + row;
       const bool valid = grow < g.M;
-      float *hrow = g.h + grow * H + c0;
+      const bool pvalid = (int64_t)panel * 128 < g.M;              // false: the phantom second panel of an odd count
+      // panel layout: cell (c4, row) = 16 bytes at ((c4 * 128) + row) * 16; this thread: c4 = c0 / 4 + ...
+      float *hrow = g.h + (int64_t)panel * (128 * H) + (c0 >> 2) * 512 + row * 4;
       const float *cs = g.cond;
-      if (valid) {
-        // pull this thread's piece of the residual stream and the FiLM row of its crystal towards L2
+      if (pvalid) {
+        // pull this warp's piece of the residual stream (32 c4 blocks of 512 bytes) towards L2
+        const char *hw = reinterpret_cast<const char *>(g.h + (int64_t)panel * (128 * H) + (c0 >> 2) * 512 + q * 128);
 #pragma unroll
-        for (int l = 0; l < 4; l++) prefetch_l2(reinterpret_cast<const char *>(hrow) + l * 128);
+        for (int l = 0; l < 4; l++) prefetch_l2(hw + ((lane + 32 * l) >> 2) * 2048 + ((lane + 32 * l) & 3) * 128);
+      }
+      if (valid) {
+        // ... and the FiLM row of this thread's crystal
         if (g.do_film) {
           cs = g.cond + ((grow / g.N) * g.B + g.node2graph[(int)(grow % g.N)]) * H2;
 #pragma unroll
@@ -313,6 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
         mbar_wait(acc_all, n_all & 1);
         n_all++;
         tc_fence_after_sync();
+        N2_ESTAMP(16);
         {
           uint32_t accA[16], accB[16];
           tmem_ld16(taddr, accA);
@@ -326,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             uint32_t w[8];
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn1 + c + 4 * j4));
+              const float4 b = ld_param4(g.bn1 + c + 4 * j4);
               w[2 * j4] = pack_half2(silu_fast(__uint_as_float(acc[4 * j4]) + b.x), silu_fast(__uint_as_float(acc[4 * j4 + 1]) + b.y));
               w[2 * j4 + 1] = pack_half2(silu_fast(__uint_as_float(acc[4 * j4 + 2]) + b.z), silu_fast(__uint_as_float(acc[4 * j4 + 3]) + b.w));
             }
@@ -335,23 +413,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           }
         }
         signal(x_ready_dst, true);
+        N2_ESTAMP(17);
         // ---- E2: h = h + SiLU(acc + bn2) -> fp32 (global) and fp16 -> X ----
         float hv[16], hn_[16];
         auto load_h = [&](int blk, float (&dst)[16]) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) dst[j] = 0.f;
-          if (valid) {
-            float a[8], b[8];
-            ld_f8_stream(hrow + blk * 16, a);
-            ld_f8_stream(hrow + blk * 16 + 8, b);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { dst[j] = a[j]; dst[8 + j] = b[j]; }
+          for (int j4 = 0; j4 < 4; j4++) {
+#ifdef N2_EXP_NO_E2_LOAD
+            const float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+            const float4 v = pvalid ? ld_f4_stream(hrow + (blk * 4 + j4) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+            dst[4 * j4] = v.x; dst[4 * j4 + 1] = v.y; dst[4 * j4 + 2] = v.z; dst[4 * j4 + 3] = v.w;
           }
         };
         load_h(0, hn_);
         mbar_wait(acc_all, n_all & 1);
         n_all++;
         tc_fence_after_sync();
+        N2_ESTAMP(18);
 #pragma unroll 1
         for (int hb = 0; hb < 8; hb++) {
           uint32_t acc[16];
@@ -364,18 +444,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           float o[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bn2 + c + 4 * j4));
+            const float4 b = ld_param4(g.bn2 + c + 4 * j4);
             o[4 * j4] = hv[4 * j4] + silu_fast(__uint_as_float(acc[4 * j4]) + b.x);
             o[4 * j4 + 1] = hv[4 * j4 + 1] + silu_fast(__uint_as_float(acc[4 * j4 + 1]) + b.y);
             o[4 * j4 + 2] = hv[4 * j4 + 2] + silu_fast(__uint_as_float(acc[4 * j4 + 2]) + b.z);
             o[4 * j4 + 3] = hv[4 * j4 + 3] + silu_fast(__uint_as_float(acc[4 * j4 + 3]) + b.w);
           }
-          if (valid) {
-            float a[8], b[8];
+          if (g.h_rowmajor != nullptr) {          // mode TAIL: row-major, for the final LayerNorm
+            if (valid) {
+              float a[8], b[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) { a[j] = o[j]; b[j] = o[8 + j]; }
-            st_f8(hrow + hb * 16, a);
-            st_f8(hrow + hb * 16 + 8, b);
+              for (int j = 0; j < 8; j++) { a[j] = o[j]; b[j] = o[8 + j]; }
+              st_f8(g.h_rowmajor + grow * H + c + 0, a);
+              st_f8(g.h_rowmajor + grow * H + c + 8, b);
+            }
+          } else if (pvalid) {
+#ifndef N2_EXP_NO_E2_STORE
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++)
+              st_f4_stream(hrow + (hb * 4 + j4) * 512, make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]));
+#endif
           }
           if (g.do_film) {
             uint32_t w[8];
@@ -386,12 +474,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           }
         }
         signal(x_ready_dst, g.do_film != 0);
+        N2_ESTAMP(19);
       }
       if (g.do_film) {
         // ---- E3: FiLM + residual + layer LayerNorm on y = acc + bp (three passes over TMEM) ----
         mbar_wait(acc_all, n_all & 1);
         n_all++;
         tc_fence_after_sync();
+        N2_ESTAMP(20);
         float s = 0.f, ss = 0.f;
         {
           uint32_t accA[16], accB[16];
@@ -404,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             if (hb < 7) tmem_ld16(taddr + (hb + 1) * 16, nxt);
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bp + c0 + hb * 16 + 4 * j4));
+              const float4 b = ld_param4(g.bp + c0 + hb * 16 + 4 * j4);
               const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int k = 0; k < 4; k++) {
@@ -431,6 +521,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           mean1 = ts * (1.0f / H);
           rstd1 = rsqrtf(fmaxf(tss * (1.0f / H) - mean1 * mean1, 0.f) + 1e-5f);
         }
+        N2_ESTAMP(21);
         // pass 2: f = SiLU(LN(y) scale + shift), h += f (global, and kept in TMEM), statistics of the new h
         s = 0.f;
         ss = 0.f;
@@ -438,13 +529,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           float hv[16], hn_[16];
           auto load_h = [&](int blk, float (&dst)[16]) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) dst[j] = 0.f;
-            if (valid) {
-              float a[8], b[8];
-              ld_f8_stream(hrow + blk * 16, a);
-              ld_f8_stream(hrow + blk * 16 + 8, b);
-#pragma unroll
-              for (int j = 0; j < 8; j++) { dst[j] = a[j]; dst[8 + j] = b[j]; }
+            for (int j4 = 0; j4 < 4; j4++) {
+              const float4 v = pvalid ? ld_f4_stream(hrow + (blk * 4 + j4) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+              dst[4 * j4] = v.x; dst[4 * j4 + 1] = v.y; dst[4 * j4 + 2] = v.z; dst[4 * j4 + 3] = v.w;
             }
           };
           load_h(0, hn_);
@@ -459,15 +546,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             float4 sc[4], sh[4];
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              sc[j4] = __ldg(reinterpret_cast<const float4 *>(cs + col0 + 4 * j4));
-              sh[j4] = __ldg(reinterpret_cast<const float4 *>(cs + H + col0 + 4 * j4));
+              sc[j4] = N2_COND(cs + col0 + 4 * j4);
+              sh[j4] = N2_COND(cs + H + col0 + 4 * j4);
             }
             tmem_ld_wait();
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              const float4 pb = __ldg(reinterpret_cast<const float4 *>(g.bp + col0 + 4 * j4));
-              const float4 pg = __ldg(reinterpret_cast<const float4 *>(g.g1 + col0 + 4 * j4));
-              const float4 pbb = __ldg(reinterpret_cast<const float4 *>(g.b1 + col0 + 4 * j4));
+              const float4 pb = ld_param4(g.bp + col0 + 4 * j4);
+              const float4 pg = ld_param4(g.g1 + col0 + 4 * j4);
+              const float4 pbb = ld_param4(g.b1 + col0 + 4 * j4);
               const float bps[4] = {pb.x, pb.y, pb.z, pb.w}, g1s[4] = {pg.x, pg.y, pg.z, pg.w};
               const float b1s[4] = {pbb.x, pbb.y, pbb.z, pbb.w};
               const float scs[4] = {sc[j4].x, sc[j4].y, sc[j4].z, sc[j4].w};
@@ -484,16 +571,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
               }
             }
             tmem_st16(taddr + blk * 16, acc);
-            if (valid) {
-              float a[8], b[8];
+#ifndef N2_EXP_NO_P2_STORE
+            if (pvalid) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) { a[j] = __uint_as_float(acc[j]); b[j] = __uint_as_float(acc[8 + j]); }
-              st_f8(hrow + blk * 16, a);
-              st_f8(hrow + blk * 16 + 8, b);
+              for (int j4 = 0; j4 < 4; j4++)
+                st_f4_stream(hrow + (blk * 4 + j4) * 512, make_float4(__uint_as_float(acc[4 * j4]), __uint_as_float(acc[4 * j4 + 1]),
+                                                                      __uint_as_float(acc[4 * j4 + 2]), __uint_as_float(acc[4 * j4 + 3])));
             }
+#endif
           }
         }
         tmem_st_wait();
+        N2_ESTAMP(22);
         slot[2] = s;
         slot[3] = ss;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -525,8 +614,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             uint32_t w[8];
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              const float4 pg = __ldg(reinterpret_cast<const float4 *>(g.g2 + c + 4 * j4));
-              const float4 pb = __ldg(reinterpret_cast<const float4 *>(g.b2 + c + 4 * j4));
+              const float4 pg = ld_param4(g.g2 + c + 4 * j4);
+              const float4 pb = ld_param4(g.b2 + c + 4 * j4);
               const float a0 = fmaf((__uint_as_float(acc[4 * j4]) - mean2) * rstd2, pg.x, pb.x);
               const float a1 = fmaf((__uint_as_float(acc[4 * j4 + 1]) - mean2) * rstd2, pg.y, pb.y);
               const float a2 = fmaf((__uint_as_float(acc[4 * j4 + 2]) - mean2) * rstd2, pg.z, pb.z);
@@ -538,12 +627,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             *reinterpret_cast<uint4 *>(xrow + (c >> 3) * 2048) = lo;
             *reinterpret_cast<uint4 *>(xrow + ((c >> 3) + 1) * 2048) = hi;
             if (valid) {
-              *reinterpret_cast<uint4 *>(dst + (hb * 2) * 1024) = lo;
-              *reinterpret_cast<uint4 *>(dst + (hb * 2 + 1) * 1024) = hi;
+              st_u4_stream(dst + (hb * 2) * 1024, lo);
+              st_u4_stream(dst + (hb * 2 + 1) * 1024, hi);
             }
           }
         }
         signal(x_ready_dst, true);
+        N2_ESTAMP(23);
         // ---- E4: the four units of P = hn [W_hi ; W_hj]^T -> fp16 row-major; this warp: 64 columns per unit ----
         __half *prow = g.P + grow * H2 + cgp * 64;
 #pragma unroll 1
@@ -551,6 +641,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
           const int hf = u & 1;
           mbar_wait(acc_full(hf), (uint32_t)(u >> 1));       // two completions per panel and half: units hf, hf + 2
           tc_fence_after_sync();
+          N2_ESTAMP(24 + 2 * u);
           const uint32_t ta = tq + 256 * hf + cgp * 64;
           uint32_t accA[16], accB[16];
           tmem_ld16(ta, accA);
@@ -566,14 +657,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             if (valid) st_u8(prow + u * 256 + hb * 16, w);
           }
           signal(leader ? acc_empty(hf) : mapa_shared(acc_empty(hf), 0), false);
+          N2_ESTAMP(25 + 2 * u);
         }
       }
+#ifdef CB2_NODE_TIMELINE
+      eit++;
+#endif
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();               // nobody leaves while the peer's MMAs / TMA may still touch this CTA
   if (warp == 1) tmem_dealloc2(tmem, 512);
+}
+
+int debug_node2_timeline(long long *out64x3) {
+  CB2_CUDA_OK(cudaMemcpyFromSymbol(out64x3, g_node2_dbg, sizeof(long long) * 3 * 64));
+  return CB2_OK;
 }
 
 // a row-panel activation buffer as a sequence of 16 KB chunks (128 rows x K 64, already in operand order):
@@ -583,8 +683,8 @@ static int encode_chunk_map(CUtensorMap *tm, const void *base, uint64_t bytes) {
 }
 
 int launch_tc_node2(const cb2_model *m, const cb2_layer_weights *Lmlp, const cb2_layer_weights *Lfilm,
-                    const cb2_batch *b, const float *film_cond, float *h, const __half *h16, __half *cat16, __half *P,
-                    int n_sm, cudaStream_t st) {
+                    const cb2_batch *b, const float *film_cond, float *h, float *h_rowmajor, const __half *h16,
+                    __half *cat16, __half *P, int n_sm, cudaStream_t st) {
   const int64_t VN = (int64_t)b->n_variants * b->n_nodes;
   if (VN == 0) return CB2_OK;
   if (!Lmlp && !Lfilm) return fail(CB2_ERR_BAD_ARG, "tc_node2: nothing to do");
@@ -593,7 +693,8 @@ int launch_tc_node2(const cb2_model *m, const cb2_layer_weights *Lmlp, const cb2
   a.M = VN; a.n_pairs = (int)((n_panels + 1) / 2);
   a.do_mlp = Lmlp != nullptr; a.do_film = Lfilm != nullptr;
   a.N = b->n_nodes; a.B = b->n_graphs; a.node2graph = b->node2graph; a.cond = film_cond;
-  a.h = h; a.cat16 = cat16; a.P = P;
+  a.h = h; a.h_rowmajor = Lfilm ? nullptr : h_rowmajor; a.cat16 = cat16; a.P = P;
+  if (!Lfilm && !h_rowmajor) return fail(CB2_ERR_BAD_ARG, "tc_node2: mode TAIL needs the row-major output");
   // a map the launch does not use still has to be a valid descriptor: it points at the FiLM projection image
   CUtensorMap tm_cat, tm_h16, tm_wn1, tm_wn2, tm_wp, tm_whij;
   CB2_TRY(encode_weight_map(&tm_wp, m->film_wp_t, H, H / 8, 128, 8));
