@@ -264,15 +264,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
       // acc_empty(hf) completes twice per panel: units hf (phase parity 0) and hf + 2 (parity 1) have been drained
       auto wait_half = [&](int hf, uint32_t parity) { mbar_wait_spin(acc_empty(hf), parity); };
       // a GEMM with all 512 output columns, K = 64 nk: A chunk kc from X (streamed = through the A ring)
+#ifdef CB2_NODE_TIMELINE
+      long long tw_a = 0, tw_w = 0, tw_i = 0;      // G1 of a panel: cycles waiting for A, for W, issuing
+#define N2_TCLK() clock64()
+#else
+#define N2_TCLK() 0
+#endif
       auto gemm512 = [&](int nk, bool streamed) {
         for (int kc = 0; kc < nk; kc++) {
           uint32_t a_off = (uint32_t)kc * N2_CH_BYTES;
+          [[maybe_unused]] const long long c0 = N2_TCLK();
           if (streamed) {
             const int s = (int)(ca % N2_ASLOTS);
             mbar_wait_spin(a_full(s), (ca / N2_ASLOTS) & 1);
             a_off = (uint32_t)s * N2_CH_BYTES;
           }
+          [[maybe_unused]] const long long c1 = N2_TCLK();
           const uint32_t w_off = wait_w();
+          [[maybe_unused]] const long long c2 = N2_TCLK();
           tc_fence_after_sync();
           issue_box(a_off, w_off, 0, kc == 0);
           issue_box(a_off, w_off + N2_CH_BYTES, 256, kc == 0);
@@ -281,6 +290,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
             ca++;
           }
           done_w();
+#ifdef CB2_NODE_TIMELINE
+          if (streamed) { tw_a += c1 - c0; tw_w += c2 - c1; tw_i += clock64() - c2; }
+#endif
         }
         umma2_commit_mc(acc_all, (uint16_t)3);
       };
@@ -295,6 +307,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N2_THREADS, 1)
         if (g.do_mlp) {
           gemm512(16, true);                    // G1
           N2_STAMP(it, 1);
+#ifdef CB2_NODE_TIMELINE
+          if (blockIdx.x == 0 && g.do_film && it >= 1 && it <= 3) {
+            g_node2_dbg[(it - 1) * 64 + 40] = tw_a; g_node2_dbg[(it - 1) * 64 + 41] = tw_w; g_node2_dbg[(it - 1) * 64 + 42] = tw_i;
+          }
+          tw_a = tw_w = tw_i = 0;
+#endif
           wait_x();                             // E1: X = z
           N2_STAMP(it, 2);
           tc_fence_after_sync();

@@ -45,3 +45,4 @@ if os.environ.get("CB2_TIMELINE"):
         base = t[itx, 0]
         ev = sorted((int(t[itx, k] - base), names[k]) for k in names if t[itx, k] != 0)
         print("panel", itx + 1, " | ".join(f"{nm}@{tt}" for tt, nm in ev))
+        print("  G1 issuer: waiting for A", t[itx, 40], "for W", t[itx, 41], "issuing", t[itx, 42])

@@ -2,7 +2,7 @@
 import re, sys
 for line in sys.stdin:
     if not line.startswith("panel"):
-        if "forward" in line or "variant" in line: print(line.strip())
+        if "forward" in line or "variant" in line or "issuer" in line: print(line.strip())
         continue
     ev = {m.group(1): int(m.group(2)) for m in re.finditer(r"((?:mma|epi):[^@|]+)@(\d+)", line)}
     g = lambda k: ev.get(k, 0)
