@@ -214,6 +214,11 @@ def main():
     ap.add_argument("--single-cta-edge", action="store_true", help="A/B: one-CTA edge kernel instead of the CTA-pair kernel")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(0, args.warmup)
+    # stdout carries exactly ONE JSON line: anything a library writes to file descriptor 1 (NCCL prints its version
+    # banner there at every debug level the environment may set) is sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,7 +257,7 @@ def main():
                                  "sample": sample},
                 "e2e": {"value": v, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import numpy as np
@@ -260,8 +265,6 @@ def main():
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import ctypes as C
@@ -362,6 +365,43 @@ def main():
     finite = bool(torch.isfinite(run.x).all() and torch.isfinite(run.l).all())
     value = Bg / (ms_step * 1e-3 * T_STEPS)
 
+    # ---------------- in-step kernel shares (CUPTI activity trace of a few more graph replays) ----------------
+    # The timestep runs at the board's power limit, so a kernel inside it is slower than the same kernel timed alone;
+    # the share of the step a kernel takes has to be measured IN the step (ncu's launch list, the other witness,
+    # is serialised and cold-cache).  Outside the timed region; rank 0 only.
+    def trace_in_step():
+        in_step = None
+        if not (rank == 0 and want_roof):
+            return None
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            for _ in range(6):             # back to the power-limited steady state of the timed region
+                run.step()
+            torch.cuda.synchronize()
+            n_tr = 3
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(n_tr):
+                    run.step()
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+            if evs:
+                span = max(e.time_range.end for e in evs) - min(e.time_range.start for e in evs)
+                per = {}
+                for e in evs:
+                    k = e.name.split("(")[0].replace("cb2::", "")
+                    c = per.setdefault(k, [0, 0.0])
+                    c[0] += 1
+                    c[1] += e.time_range.end - e.time_range.start
+                in_step = {"ms_per_step": span / n_tr / 1e3,
+                           "kernels": {k: {"launches_per_step": c[0] / n_tr, "ms_per_launch": c[1] / c[0] / 1e3,
+                                           "share_of_step": c[1] / span}
+                                       for k, c in sorted(per.items(), key=lambda kv: -kv[1][1])[:6]},
+                           "source": f"CUPTI kernel activity of {n_tr} graph replays right after the timed steps"}
+        except Exception as exc:          # profiling aid only: never fails the bench
+            in_step = {"error": repr(exc)[:200]}
+        return in_step
+
+
     # ---------------- end to end through the public API ----------------
     e2e = None
     parity = None
@@ -423,8 +463,10 @@ def main():
     # ---------------- dominant kernel (roofline) ----------------
     peaks = measured_peaks()
     roof = None
+    in_step = None
     if want_roof:
         ms_hot = time_edge_kernel()          # again, right after the timed steps (board at its power limit)
+        in_step = trace_in_step()
         flops = topo.V * topo.E * EDGE_FLOP_PER_EDGE_LAYER
         ach = flops / (ms_edge_alone * 1e-3) / 1e12
         ach_hot = flops / (ms_hot * 1e-3) / 1e12
@@ -441,7 +483,19 @@ def main():
                 "after_timed_steps": {"ms_per_launch": ms_hot, "achieved": ach_hot,
                                       "frac_of_sustained_peak": ach_hot / peaks.get("bf16_tflops_sustained", peak)},
                 "share_of_step": 12 * ms_hot / my_ms,
+                "share_source": "12 x the stand-alone launch time / ms_per_step",
                 "tile_fill": topo.E / max(1, topo.n_tiles * 128)}
+        ek = "k_tc_edge" if (args.single_cta_edge or topo.V == 1) else "k_tc_edge2"
+        if in_step and ek in in_step.get("kernels", {}):
+            # inside the step the kernel runs at the sustained (power-limited) clock: that share is the one that
+            # has to agree with the ncu launch list under profiles/
+            ik = in_step["kernels"][ek]
+            roof["share_of_step"] = ik["share_of_step"]
+            roof["share_source"] = in_step["source"]
+            roof["in_step"] = {"ms_per_launch": ik["ms_per_launch"],
+                               "achieved": flops / (ik["ms_per_launch"] * 1e-3) / 1e12,
+                               "frac_of_sustained_peak": flops / (ik["ms_per_launch"] * 1e-3) / 1e12 /
+                                                         peaks.get("bf16_tflops_sustained", peak)}
     step_flops = 4 * sum(forward_flops(n) for n in nat_global)
     step_tflops = step_flops / (ms_step * 1e-3) / 1e12
 
@@ -467,14 +521,14 @@ def main():
         "gpu_launches": int(launches_per_step) * K, "launches_per_step": int(launches_per_step),
         "roofline": roof, "cpu_baseline": cpu,
         "algorithmic_tflops": step_tflops, "state_finite": finite,
-        "parity_at_scale": parity, "rank_ms_per_step": rank_ms,
+        "parity_at_scale": parity, "rank_ms_per_step": rank_ms, "in_step": in_step,
         "latency_ms_per_1000_steps": ms_step * T_STEPS,
     }
     if world > 1:
         line["shard_invariant"] = bool(parity and parity["ok"])
         line["partition_cost_spread"] = (max(plan.cost(r) for r in range(world)) /
                                          max(1e-9, min(plan.cost(r) for r in range(world))))
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -11,8 +11,8 @@ def launches(path, out):
         v = v / 1e6 if u == 'ns' else v / 1e3 if u == 'us' else v * 1e3 if u == 's' else v
         d = agg.setdefault(name, [0, 0.0]); d[0] += 1; d[1] += v; tot += v
     with open(out, 'w') as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-roofline`\n")
-        f.write("# (the first 110 launches: two decoder forwards and a bit; per-launch times are cold-cache and serialised: compare SHARES)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-roofline --no-e2e`\n")
+        f.write("# (warm-up timestep + one timed timestep; per-launch times are cold-cache and serialised: compare SHARES)\n")
         f.write(f"{'kernel':58s} {'launches':>8s} {'total ms':>10s} {'avg ms':>9s} {'share':>7s}\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:58]:58s} {c:8d} {t:10.3f} {t/c:9.4f} {100*t/tot:6.1f}%\n")
@@ -43,10 +43,10 @@ def full(rep, out, title, index=0):
             f.write(f"{h:72s} {v:.3f}\n")
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches_r1.csv", "profiles/r1_launches.txt")
-    rep = "gpurun_out/full_r1c.ncu-rep"   # -k regex:k_tc_(edge|linear|film) -s 4 -c 5: MLP2 of one layer, then the next CSPLayer
-    full(rep, "profiles/r1_k_tc_edge_full.txt", "k_tc_edge, C3 (B=4096, n=20, cond+null), one CSPLayer", 3)
-    full(rep, "profiles/r1_k_tc_film_full.txt", "k_tc_film, fused FiLM projection + FiLM + residual + LayerNorms (M=163840, N=K=512)", 1)
-    full(rep, "profiles/r1_k_tc_linear_hoist_full.txt", "k_tc_linear, hoisted [W_hi;W_hj] GEMM (M=163840 N=1024 K=512, per-crystal bias)", 2)
-    full(rep, "profiles/r1_k_tc_linear_mlp1_full.txt", "k_tc_linear, node MLP layer 1 (M=163840 N=512 K=1024, SiLU, fp16 panel output)", 4)
-    full(rep, "profiles/r1_k_tc_linear_mlp2_full.txt", "k_tc_linear, node MLP layer 2 (M=163840 N=512 K=512, SiLU + residual, fp32 + fp16 outputs)", 0)
+    # round 2, final state: `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-roofline --no-e2e`
+    launches("gpurun_out/r2f_launches.csv", "profiles/r2_launches.txt")
+    rep = "gpurun_out/r2f_full.ncu-rep"    # -k regex:k_tc_(edge2|node2) -s 10 -c 5: FULL, edge, TAIL, HEAD, edge
+    full(rep, "profiles/r2_edge_full.txt", "k_tc_edge2 (CTA pair, cta_group::2), C3 (B=4096, n=20, cond+null), one CSPLayer", 1)
+    full(rep, "profiles/r2_node2_full.txt", "k_tc_node2 mode FULL (node MLP of layer l, FiLM block + LayerNorm + hoist GEMM of layer l+1), C3: 163 840 rows", 0)
+    full(rep, "profiles/r2_node2_tail.txt", "k_tc_node2 mode TAIL (node MLP of the last layer), C3: 163 840 rows", 2)
+    full(rep, "profiles/r2_node2_head.txt", "k_tc_node2 mode HEAD (FiLM block + LayerNorm + hoist GEMM of the first layer), C3: 163 840 rows", 3)
