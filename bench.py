@@ -373,6 +373,8 @@ def main():
         in_step = None
         if not (rank == 0 and want_roof):
             return None
+        if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR")):
+            return {"error": "running under a profiler that owns CUPTI: no in-step trace"}
         try:
             from torch.profiler import ProfilerActivity, profile
             for _ in range(6):             # back to the power-limited steady state of the timed region
