@@ -30,14 +30,28 @@ except Exception:  # pragma: no cover
     HAVE_ASE = False
 
 
+_PBC = np.array([True, True, True])
+_PBC.setflags(write=False)
+
+
 class AtomsLite:
     """Stand-in for ase.Atoms when ase is not importable."""
+
+    __slots__ = ("numbers", "cell", "_scaled", "pbc")
 
     def __init__(self, numbers, cell, scaled_positions, pbc=True):
         self.numbers = np.asarray(numbers, dtype=np.int64)
         self.cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
         self._scaled = np.asarray(scaled_positions, dtype=np.float64).reshape(-1, 3)
         self.pbc = np.array([pbc] * 3)
+
+    @classmethod
+    def _from_views(cls, numbers, cell, scaled_positions):
+        """Batch boundary: the arguments are already int64 [n] / float64 [3,3] / float64 [n,3] slices of the batch
+        arrays (no per-structure conversion: 32 768 structures are built on rank 0 after every multi-GPU job)."""
+        o = cls.__new__(cls)
+        o.numbers, o.cell, o._scaled, o.pbc = numbers, cell, scaled_positions, _PBC
+        return o
 
     def get_scaled_positions(self):
         return self._scaled
@@ -77,8 +91,9 @@ def batch_symbol_order(a: np.ndarray, natoms: Sequence[int]) -> np.ndarray:
     """`symbol_sort_order` of every crystal of a batch in one vectorised stable sort: global atom
     indices, crystal by crystal, each crystal's atoms ordered by (symbol string, original index)."""
     nat = np.asarray(natoms, dtype=np.int64)
-    crystal = np.repeat(np.arange(len(nat)), nat)
-    return np.lexsort((np.arange(a.shape[0]), _SYMBOL_RANK[a], crystal))
+    crystal = np.repeat(np.arange(len(nat), dtype=np.int64), nat)
+    # one integer key (crystal, symbol rank < 128) and a STABLE sort: equal symbols keep their original order
+    return np.argsort(crystal * 128 + _SYMBOL_RANK[a], kind="stable")
 
 
 def state_to_atoms(atom_types: np.ndarray, frac_coords: np.ndarray, lattices: np.ndarray,
@@ -97,9 +112,10 @@ def state_to_atoms(atom_types: np.ndarray, frac_coords: np.ndarray, lattices: np
         return out
     order = batch_symbol_order(a, natoms)
     z_sorted = a[order]
-    x_sorted = np.asarray(frac_coords, dtype=np.float64)[order]
+    x_sorted = np.asarray(frac_coords)[order].astype(np.float64)
     lat = lat.astype(np.float64)
+    make = AtomsLite._from_views
     for i, n in enumerate(natoms):
-        out.append(AtomsLite(z_sorted[off:off + n], lat[i], x_sorted[off:off + n]))
+        out.append(make(z_sorted[off:off + n], lat[i], x_sorted[off:off + n]))
         off += n
     return out
