@@ -23,25 +23,37 @@ def sample_cost(n: int) -> float:
 def partition_samples(natoms: Sequence[int], world_size: int) -> List[List[int]]:
     """Deterministic LPT assignment of sample indices to ranks; each rank's list is
     sorted by (n, index) so equal-size crystals are contiguous (tile regularity)."""
-    order = sorted(range(len(natoms)), key=lambda i: (-int(natoms[i]), i))
-    loads = [0.0] * world_size
+    import heapq
+
+    nat = np.asarray(natoms, dtype=np.int64)
+    order = np.lexsort((np.arange(len(nat)), -nat))              # (-n, index)
+    if world_size == 1:
+        return [np.lexsort((np.arange(len(nat)), nat)).tolist()]
+    cost = (nat * nat + 2.4 * nat).tolist()                       # sample_cost, vectorised
+    heap = [(0.0, r) for r in range(world_size)]                  # least loaded rank first, ties by rank
     parts: List[List[int]] = [[] for _ in range(world_size)]
-    for i in order:
-        r = min(range(world_size), key=lambda k: (loads[k], k))
+    for i in order.tolist():
+        load, r = heapq.heappop(heap)
         parts[r].append(i)
-        loads[r] += sample_cost(int(natoms[i]))
-    for p in parts:
-        p.sort(key=lambda i: (int(natoms[i]), i))
+        heapq.heappush(heap, (load + cost[i], r))
+    for r, p in enumerate(parts):
+        pa = np.asarray(p, dtype=np.int64)
+        parts[r] = pa[np.lexsort((pa, nat[pa]))].tolist() if len(p) else []
     return parts
 
 
 def node_slices(natoms: Sequence[int], idx: Sequence[int]) -> np.ndarray:
     """Global node indices of the samples `idx`, in that order."""
-    off = np.zeros(len(natoms) + 1, dtype=np.int64)
-    np.cumsum(np.asarray(natoms, dtype=np.int64), out=off[1:])
-    if len(idx) == 0:
+    nat = np.asarray(natoms, dtype=np.int64)
+    off = np.zeros(len(nat) + 1, dtype=np.int64)
+    np.cumsum(nat, out=off[1:])
+    idx = np.asarray(idx, dtype=np.int64)
+    if idx.size == 0:
         return np.zeros(0, dtype=np.int64)
-    return np.concatenate([np.arange(off[i], off[i + 1]) for i in idx])
+    lens = nat[idx]
+    first = np.zeros(len(idx), dtype=np.int64)                    # position of each sample's first node in the output
+    np.cumsum(lens[:-1], out=first[1:])
+    return np.repeat(off[idx] - first, lens) + np.arange(int(lens.sum()), dtype=np.int64)
 
 
 def gather_structures(a: torch.Tensor, x: torch.Tensor, l: torch.Tensor, natoms: Sequence[int],
