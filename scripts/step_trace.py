@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
 
+from chemeleon_b200 import _lib
+if os.environ.get("CB2_LIB"):
+    _lib.LIB_PATH = os.environ["CB2_LIB"]      # development: a variant build of the library
 from chemeleon_b200 import dist as cdist
 from chemeleon_b200.config import SamplerConfig
 from chemeleon_b200.sampler import ChemeleonB200
