@@ -74,8 +74,15 @@ int cb2_pack_weights(int32_t kind, const float *w, int32_t rows, int32_t K, void
     }
     case CB2_PACK_ROW_BLOCKS:
       // one K-major image per block of 128 output rows: [rows/128][K/8][128][8]
+      // ... of w / 2 (exact in fp16): the GEMM2 accumulator of the edge kernels then holds the x / 2 that the tanh
+      // form of SiLU starts from (cb2_tc.cuh silu_of_half)
       if (rows % 128 != 0) return fail(CB2_ERR_BAD_ARG, "pack_weights: row blocks need rows % 128 == 0");
-      for (int b = 0; b < rows / 128; b++) kmajor(w + (int64_t)b * 128 * K, 128, K, K, o + (int64_t)b * 128 * K, nullptr);
+      {
+        std::vector<float> half((size_t)rows * K);
+        for (int64_t i = 0; i < (int64_t)rows * K; i++) half[i] = 0.5f * w[i];
+        for (int b = 0; b < rows / 128; b++)
+          kmajor(half.data() + (int64_t)b * 128 * K, 128, K, K, o + (int64_t)b * 128 * K, nullptr);
+      }
       return CB2_OK;
     case CB2_PACK_HEAD_SPLIT: {
       // 16-byte header {float 1/s} + K-major image [3K/8][256][8] of s [w_hi | w_hi | w_lo] (rows >= `rows` zero);

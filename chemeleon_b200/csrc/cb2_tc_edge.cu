@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) k_tc_edge(TcEdgeArgs g) {
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + u4 * 128;
     const int c = u4 * 128 + q * 32 + lane;      // output channel owned in the epilogues
     const __half *Pc = g.P + c;
-    const float bias = __ldg(g.b2 + c);
+    const float bias = 0.5f * __ldg(g.b2 + c);      // the units hold (W2 a1 + b2) / 2 (cb2_tc.cuh silu_of_half)
     const int oc = g.agg_col + c;
     __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
     const AggStride agg_ld = g.agg_kt > 0 ? AggStride{(int64_t)128 * g.agg_kt, 8, 0u}

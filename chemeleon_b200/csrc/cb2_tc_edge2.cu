@@ -312,11 +312,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
     const uint32_t a1_off = sbase + (uint32_t)((c1 / 8) * 2048 + (c1 % 8) * 16);
     const A1Dst a1_dst = e_v == (int)rank ? A1Dst{a1_off, 0u}
                                           : A1Dst{mapa_shared(a1_off, rank ^ 1u), mapa_shared(a1_rx, rank ^ 1u)};
-    const float bias_o1 = __ldg(g.b2 + 256 * rank + 128 + q * 32 + lane);     // O1 re-uses the X columns
+    // the O units hold (W2 a1 + b2) / 2: image of W2 / 2, pre-loaded with b2 / 2 (cb2_tc.cuh silu_of_half)
+    const float bias_o1 = 0.5f * __ldg(g.b2 + 256 * rank + 128 + q * 32 + lane);     // O1 re-uses the X columns
     // E2
     const uint32_t taddr_o = tq + (e_u == 0 ? 256 : 0) + 128 * e_v;
     const int co = 256 * (int)rank + 128 * e_u + q * 32 + lane;
-    const float bias_o = __ldg(g.b2 + co);
+    const float bias_o = 0.5f * __ldg(g.b2 + co);
     const int oc = g.agg_col + co;
     __half *out = g.agg_kt > 0 ? g.agg16 + (int64_t)(oc >> 3) * 1024 + (oc & 7) : g.agg16 + oc;
     const uint32_t vrow = (uint32_t)e_v * (uint32_t)g.N;

@@ -57,7 +57,7 @@ __device__ __noinline__ void e2_unit(int n_rt, uint32_t taddr, float bias, const
     // fp32 tanh here (one MUFU op per element): the paired fp16 form (tanh.approx.f16x2, one MUFU op per two
     // SiLUs) was measured slower in both edge kernels (more issue slots: E2 is latency / issue bound) at 1.5x
     // the error, and the mean is better taken over unrounded values
-    for (int j = 0; j < 32; j++) t[j] = silu_fast(__uint_as_float(acc[j]));   // b2 is already in the accumulator
+    for (int j = 0; j < 32; j++) t[j] = silu_of_half(__uint_as_float(acc[j]));   // the accumulator holds (W2 a1 + b2) / 2
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       sum += t[j];

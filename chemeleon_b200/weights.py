@@ -274,7 +274,9 @@ def pack_weights(source, cfg: Optional[SamplerConfig] = None, device="cuda", ten
             wn1=d(wn1), bn1=d(get(p + ".node_mlp.0.bias")),
             wn2=d(wn2), bn2=d(get(p + ".node_mlp.2.bias")),
             ln_g=d(get(p + ".layer_norm.weight")), ln_b=d(get(p + ".layer_norm.bias")),
-            w_hij_t=tiled(w_hij), w_fd_t=tiled(w_fd[:, perm]), w2_t=tiled_blocks(w2),
+            w_hij_t=tiled(w_hij), w_fd_t=tiled(w_fd[:, perm]),
+            w2_t=tiled_blocks(w2 * 0.5),      # image of W2 / 2 (exact in fp16): the GEMM2 accumulator is the x / 2 of SiLU's tanh form
+
             wn1_t=tiled(wn1), wn2_t=tiled(wn2)))
 
     A = cfg.max_atoms

@@ -69,7 +69,7 @@ typedef struct {
   const float *ln_b;
   /* fp16 tcgen05 operand images (K-major, no swizzle: [K/8][rows][8]); NULL when only exact mode is
    * used.  w_fd_t has its K columns permuted to d*256 + 2k + {sin,cos} (weights.fd_column_order);
-   * w2_t is stored as four images of 128 output channels each: [4][64][128][8]. */
+   * w2_t is the image of edge_mlp.2.weight / 2, stored as four images of 128 output channels each: [4][64][128][8]. */
   const void *w_hij_t, *w_fd_t, *w2_t, *wn1_t, *wn2_t;
 } cb2_layer_weights;
 
@@ -201,7 +201,8 @@ int cb2_check_device(int device);            /* CB2_OK iff compute capability 10
  *   CB2_PACK_KMAJOR      [K/8][rows][8]  ("K-major, no swizzle": core matrix = 8 rows x 16 B)   w_hij_t, wn1_t, wn2_t, film_wp_t
  *   CB2_PACK_FD          the same with the K columns of W_fd permuted from the reference order (sin block | cos block,
  *                        cspnet.py:49-51) to d*2F + 2k + {sin,cos}                              w_fd_t
- *   CB2_PACK_ROW_BLOCKS  one K-major image per block of 128 rows: [rows/128][K/8][128][8]        w2_t
+ *   CB2_PACK_ROW_BLOCKS  one K-major image per block of 128 rows, of w / 2 (exact; the edge kernels'
+ *                        GEMM2 accumulates x / 2 for SiLU(x) = x/2 (1 + tanh(x/2))): [rows/128][K/8][128][8]  w2_t
  *   CB2_PACK_HEAD_SPLIT  16-byte header {float 1/s} + image [3K/8][256][8] of s [w_hi | w_hi | w_lo]
  *                        (split precision, power-of-two scale s, rows padded to 256)             w_head_t */
 #define CB2_PACK_KMAJOR 0

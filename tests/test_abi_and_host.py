@@ -254,7 +254,7 @@ def test_pack_weights_c_matches_python_packer(lib):
     assert torch.equal(c_pack(_lib.PACK_FD, wfd).view(torch.int16),
                        tile_k_major(wfd[:, fd_column_order(128)]).reshape(-1).view(torch.int16))
     w2 = torch.randn(512, 512, generator=g) * 0.04
-    blocks = torch.cat([tile_k_major(w2[i:i + 128]) for i in range(0, 512, 128)], dim=0)
+    blocks = torch.cat([tile_k_major(0.5 * w2[i:i + 128]) for i in range(0, 512, 128)], dim=0)     # image of W2 / 2
     assert torch.equal(c_pack(_lib.PACK_ROW_BLOCKS, w2).view(torch.int16), blocks.reshape(-1).view(torch.int16))
     # head: same construction as weights.head_split_image
     import math
